@@ -1,0 +1,207 @@
+"""Host-side driver of the B200 hot path: one `Context` per GPU wrapping the C-ABI calls
+`mdg_counts_reduce` (K1) and `mdg_fit_batch` (K3-K7) for numpy (host) or torch-CUDA (device)
+buffers. PyTorch is used for device memory and streams only."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._abi import FIT_RESULT_DTYPE, MDG_DEVICE, MDG_HOST, NUM_RUNS, Timings, ptr
+
+BASES = "ACGT"
+OFFDIAG_COLUMNS = [r + o for r in BASES for o in BASES if r != o]  # AC,AG,AT,CA,CG,CT,GA,GC,GT,TA,TC,TG
+
+
+def _base_index(sub):
+    if len(sub) != 2 or sub[0] not in BASES or sub[1] not in BASES:
+        raise ValueError(f"substitution bases must be two of ACGT, got {sub!r}")
+    return BASES.index(sub[0]), BASES.index(sub[1])
+
+
+def _dptr(t):
+    """device pointer of a contiguous torch CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("device buffers must be contiguous CUDA tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One GPU, one stream. Not thread-safe; use one Context per host thread / process."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        handle = C.c_void_p()
+        _lib.check(self._lib.mdg_ctx_create(int(device), C.byref(handle)))
+        self._h = handle
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mdg_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle):
+        _lib.check(self._lib.mdg_ctx_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)))
+
+    def synchronize(self):
+        _lib.check(self._lib.mdg_ctx_synchronize(self._h))
+
+    def timings(self):
+        t = Timings()
+        _lib.check(self._lib.mdg_ctx_get_timings(self._h, C.byref(t)))
+        return {
+            "counts_ms": t.counts_ms, "map_ms": t.map_ms, "nuts_ms": t.nuts_ms, "ppc_ms": t.ppc_ms,
+            "assemble_ms": t.assemble_ms, "total_ms": t.total_ms, "n_launches": int(t.n_launches),
+            "leapfrogs": [int(v) for v in t.leapfrogs],
+        }
+
+    def fp64_peak_tflops(self):
+        out = C.c_double(0)
+        _lib.check(self._lib.mdg_measure_fp64_peak(self._h, C.byref(out)))
+        return out.value
+
+    # ------------------------------------------------------------------ K1
+    def counts_reduce(self, tax_id, n_alignments, is_reverse, pos0, counts16, fwd="CT", rev="GA",
+                      max_position=15, min_alignments=10, min_y_sum=10, want_noise=False, want_rows=True):
+        """counts.py:237-256 on host SoA columns (numpy). Returns a dict of numpy arrays."""
+        n = len(tax_id)
+        P = int(max_position)
+        tax_id = np.ascontiguousarray(tax_id, dtype=np.int64)
+        n_alignments = np.ascontiguousarray(n_alignments, dtype=np.uint32)
+        is_reverse = np.ascontiguousarray(is_reverse, dtype=np.uint8)
+        pos0 = np.ascontiguousarray(pos0, dtype=np.uint8)
+        counts16 = np.ascontiguousarray(counts16, dtype=np.uint32)
+        if counts16.shape != (16, n):
+            raise ValueError("counts16 must be [16][n_rows] (ref-major ACGT x ACGT)")
+        fr, fo = _base_index(fwd)
+        rr, ro = _base_index(rev)
+        out = {}
+        if want_rows:
+            out.update(
+                n_fwd_ref=np.empty(n, np.uint32), n_rev_ref=np.empty(n, np.uint32),
+                f_fwd=np.empty(n, np.float32), f_rev=np.empty(n, np.float32),
+                z=np.empty(n, np.int8), y_sum_total=np.empty(n, np.uint64), keep=np.empty(n, np.uint8),
+            )
+        out.update(
+            tax_id=np.empty(n, np.int64), n_alignments=np.empty(n, np.uint32), first_row=np.empty(n, np.int64),
+            k=np.empty((n, 2 * P), np.uint32), N=np.empty((n, 2 * P), np.uint32),
+            noise=np.empty((n, 3), np.float64) if want_noise else None,
+        )
+        n_tax = C.c_int64(0)
+        g = out.get
+        _lib.check(self._lib.mdg_counts_reduce(
+            self._h, MDG_HOST, n, ptr(tax_id), ptr(n_alignments), ptr(is_reverse), ptr(pos0), ptr(counts16), n,
+            fr, fo, rr, ro, P, int(min_alignments), int(min_y_sum),
+            ptr(g("n_fwd_ref")), ptr(g("n_rev_ref")), ptr(g("f_fwd")), ptr(g("f_rev")), ptr(g("z")),
+            ptr(g("y_sum_total")), ptr(g("keep")), ptr(out["tax_id"]), ptr(out["n_alignments"]),
+            ptr(out["first_row"]), ptr(out["k"]), ptr(out["N"]), ptr(out["noise"]), C.byref(n_tax)))
+        m = n_tax.value
+        for key in ("tax_id", "n_alignments", "first_row", "k", "N", "noise"):
+            if out[key] is not None:
+                out[key] = out[key][:m]
+        out["n_tax"] = m
+        return out
+
+    def counts_reduce_device(self, cols, outs, fwd="CT", rev="GA", max_position=15, min_alignments=10,
+                             min_y_sum=10):
+        """K1 on torch CUDA tensors. cols: tax_id(i64) n_alignments(i32 bits of u32) is_reverse(u8)
+        pos0(u8) counts16([16][n] i32). outs: dict of preallocated CUDA tensors (missing -> skipped).
+        Returns the number of kept TaxIDs (forces a stream sync)."""
+        n = cols["tax_id"].numel()
+        fr, fo = _base_index(fwd)
+        rr, ro = _base_index(rev)
+        n_tax = C.c_int64(0)
+        g = lambda k: _dptr(outs.get(k))  # noqa: E731
+        _lib.check(self._lib.mdg_counts_reduce(
+            self._h, MDG_DEVICE, n, _dptr(cols["tax_id"]), _dptr(cols["n_alignments"]), _dptr(cols["is_reverse"]),
+            _dptr(cols["pos0"]), _dptr(cols["counts16"]), cols["counts16"].stride(0),
+            fr, fo, rr, ro, int(max_position), int(min_alignments), int(min_y_sum),
+            g("n_fwd_ref"), g("n_rev_ref"), g("f_fwd"), g("f_rev"), g("z"), g("y_sum_total"), g("keep"),
+            g("tax_id"), g("n_alignments"), g("first_row"), g("k"), g("N"), g("noise"), C.byref(n_tax)))
+        return n_tax.value
+
+    # ------------------------------------------------------------------ K3-K7
+    def fit_batch(self, tax_id, k, N, cfg=None, mism12=None, noise3=None, want_samples=False,
+                  want_trace=False, want_waic=False):
+        """fits.py:428-469 for a dense batch of TaxIDs on host numpy arrays."""
+        cfg = cfg or _lib.default_config()
+        tax_id = np.ascontiguousarray(tax_id, dtype=np.int64)
+        k = np.ascontiguousarray(k, dtype=np.uint32)
+        N = np.ascontiguousarray(N, dtype=np.uint32)
+        if k.ndim != 2 or k.shape != N.shape or k.shape[0] != len(tax_id) or k.shape[1] % 2:
+            raise ValueError("k and N must be [n_tax][2*max_position]")
+        n_tax, R = k.shape
+        S, W = cfg.num_samples, cfg.num_warmup
+        res = np.zeros(n_tax, dtype=FIT_RESULT_DTYPE)
+        med = np.empty((n_tax, R), np.float32)
+        lo = np.empty((n_tax, R), np.float32)
+        hi = np.empty((n_tax, R), np.float32)
+        samples = np.empty((n_tax, NUM_RUNS, S, 4)) if want_samples else None
+        trace = np.empty((n_tax, NUM_RUNS, W + S, 4)) if want_trace else None
+        waic = np.empty((n_tax, NUM_RUNS, 2, R)) if want_waic else None
+        if mism12 is not None:
+            mism12 = np.ascontiguousarray(mism12, dtype=np.uint32)
+            if mism12.shape != (n_tax, R, 12):
+                raise ValueError("mism12 must be [n_tax][2*max_position][12]")
+        if noise3 is not None:
+            noise3 = np.ascontiguousarray(noise3, dtype=np.float64)
+        _lib.check(self._lib.mdg_fit_batch(
+            self._h, MDG_HOST, n_tax, R // 2, ptr(tax_id), ptr(k), ptr(N), ptr(mism12), ptr(noise3), C.byref(cfg),
+            ptr(res), ptr(med), ptr(lo), ptr(hi), ptr(samples), ptr(trace), ptr(waic)))
+        return dict(result=res, median=med, hpdi_lo=lo, hpdi_hi=hi, samples=samples, trace=trace, waic=waic)
+
+    def fit_batch_device(self, tax_id, k, N, out, cfg=None, median=None, hpdi_lo=None, hpdi_hi=None,
+                         mism12=None, noise3=None):
+        """K3-K7 on torch CUDA tensors; `out` is a uint8 CUDA tensor of n_tax*sizeof(mdg_fit_result)."""
+        cfg = cfg or _lib.default_config()
+        n_tax, R = k.shape
+        if out.numel() * out.element_size() < n_tax * FIT_RESULT_DTYPE.itemsize:
+            raise ValueError("out buffer too small")
+        _lib.check(self._lib.mdg_fit_batch(
+            self._h, MDG_DEVICE, n_tax, R // 2, _dptr(tax_id), _dptr(k), _dptr(N), _dptr(mism12), _dptr(noise3),
+            C.byref(cfg), _dptr(out), _dptr(median), _dptr(hpdi_lo), _dptr(hpdi_hi), None, None, None))
+
+    # ------------------------------------------------------------------ test hooks
+    def lgamma_digamma(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        lg = np.empty_like(x)
+        dg = np.empty_like(x)
+        _lib.check(self._lib.mdg_test_lgamma_digamma(self._h, x.size, ptr(x), ptr(lg), ptr(dg)))
+        return lg, dg
+
+    def philox(self, key2, ctr4):
+        key2 = np.ascontiguousarray(key2, dtype=np.uint32).reshape(-1, 2)
+        ctr4 = np.ascontiguousarray(ctr4, dtype=np.uint32).reshape(-1, 4)
+        out = np.empty_like(ctr4)
+        _lib.check(self._lib.mdg_test_philox(self._h, len(ctr4), ptr(key2), ptr(ctr4), ptr(out)))
+        return out
+
+    def logp_grad(self, k, N, u, cfg=None, model=0, lane_mask=0, with_jacobian=True):
+        cfg = cfg or _lib.default_config()
+        k = np.ascontiguousarray(k, dtype=np.uint32).ravel()
+        N = np.ascontiguousarray(N, dtype=np.uint32).ravel()
+        P = len(k) // 2
+        u = np.ascontiguousarray(np.atleast_2d(u), dtype=np.float64)
+        if u.shape[1] != 4:
+            u = np.ascontiguousarray(np.pad(u, ((0, 0), (0, 4 - u.shape[1]))))
+        ne = u.shape[0]
+        logp = np.empty(ne)
+        grad = np.empty((ne, 4))
+        ll = np.empty((ne, 2 * P))
+        _lib.check(self._lib.mdg_test_logp_grad(self._h, P, ptr(k), ptr(N), C.byref(cfg), model, lane_mask,
+                                                int(with_jacobian), ne, ptr(u), ptr(logp), ptr(grad), ptr(ll)))
+        return logp, grad, ll

@@ -1,0 +1,840 @@
+// mdg_api.cu — the C-ABI of libmdgb200.so (include/mdg.h): context management, host<->device
+// staging, kernel launches and CUDA-event timing for the counts (K1) and fit (K3-K7) paths.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "mdg_counts_kernel.cuh"
+#include "mdg_post_kernels.cuh"
+
+namespace mdg {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+// grow-only device buffer
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return MDG_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return MDG_ERR_NOMEM;
+        }
+        cap = bytes;
+        return MDG_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+constexpr int kNumBufs = 24;
+constexpr int kNumEvents = 16;
+
+}  // namespace mdg
+
+struct mdg_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[mdg::kNumEvents] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    mdg::DevBuf buf[mdg::kNumBufs];
+    mdg_timings timings = {};
+};
+
+using namespace mdg;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+Priors make_priors(const mdg_fit_config& c) {
+    Priors p;
+    p.qa = c.q_prior_a; p.qb = c.q_prior_b;
+    p.Aa = c.A_prior_a; p.Ab = c.A_prior_b;
+    p.ca = c.c_prior_a; p.cb = c.c_prior_b;
+    p.rate = c.phi_prior_rate; p.phi_min = c.phi_min;
+    p.nlb_q = -(lgamma(p.qa) + lgamma(p.qb) - lgamma(p.qa + p.qb));
+    p.nlb_A = -(lgamma(p.Aa) + lgamma(p.Ab) - lgamma(p.Aa + p.Ab));
+    p.nlb_c = -(lgamma(p.ca) + lgamma(p.cb) - lgamma(p.ca + p.cb));
+    p.log_rate = log(p.rate);
+    return p;
+}
+
+// numpyro 0.4.1 hmc_util.build_adaptation_schedule: last index of every window
+int adaptation_window_ends(int num_steps, int* ends) {
+    int n = 0;
+    if (num_steps < 20) { ends[n++] = num_steps - 1; return n; }
+    int start_buffer = 75, end_buffer = 50, init_window = 25;
+    if (start_buffer + end_buffer + init_window > num_steps) {
+        start_buffer = (int)(0.15 * num_steps);
+        end_buffer = (int)(0.1 * num_steps);
+        init_window = num_steps - start_buffer - end_buffer;
+    }
+    ends[n++] = start_buffer - 1;
+    const int end_window_start = num_steps - end_buffer;
+    int next_size = init_window, next_start = start_buffer;
+    while (next_start < end_window_start && n < kMaxWindows - 1) {
+        int cur_start = next_start, cur_size = next_size;
+        if (3 * cur_size <= end_window_start - cur_start) next_size = 2 * cur_size;
+        else cur_size = end_window_start - cur_start;
+        next_start = cur_start + cur_size;
+        ends[n++] = next_start - 1;
+    }
+    ends[n++] = num_steps - 1;
+    return n;
+}
+
+template <typename K>
+int persistent_grid(K kernel, int threads, size_t smem, int num_sms, long long items, int items_per_block) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long want = (items + items_per_block - 1) / items_per_block;
+    long long cap = (long long)per_sm * num_sms;
+    return (int)std::max<long long>(1, std::min(want, cap));
+}
+
+constexpr int kNutsWarps = 4;
+constexpr int kMapWarps = 4;
+constexpr int kPpcWarps = 4;
+
+template <int MODEL, int NPL, int GW>
+int launch_nuts(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl) {
+    auto kern = nuts_kernel<MODEL, NPL, GW, kNutsWarps>;
+    int grid = persistent_grid(kern, kNutsWarps * 32, 0, ctx->num_sms, fl.n_items, kNutsWarps);
+    kern<<<grid, kNutsWarps * 32, 0, st>>>(fl);
+    MDG_CUDA_TRY(cudaGetLastError());
+    ctx->timings.n_launches++;
+    return MDG_OK;
+}
+
+template <int MODEL>
+int launch_nuts_dispatch(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl, int npl, int gw) {
+    if (gw == 16) return launch_nuts<MODEL, 1, 16>(ctx, st, fl);
+    if (npl == 1) return launch_nuts<MODEL, 1, 32>(ctx, st, fl);
+    if (npl == 2) return launch_nuts<MODEL, 2, 32>(ctx, st, fl);
+    return launch_nuts<MODEL, 4, 32>(ctx, st, fl);
+}
+
+int launch_map(mdg_ctx* ctx, cudaStream_t st, const MapLaunch& ml, int npl) {
+    const long long items = 2ll * ml.n_tax;
+    if (npl == 1) {
+        int grid = persistent_grid(map_kernel<1, kMapWarps>, kMapWarps * 32, 0, ctx->num_sms, items, kMapWarps);
+        map_kernel<1, kMapWarps><<<grid, kMapWarps * 32, 0, st>>>(ml);
+    } else if (npl == 2) {
+        int grid = persistent_grid(map_kernel<2, kMapWarps>, kMapWarps * 32, 0, ctx->num_sms, items, kMapWarps);
+        map_kernel<2, kMapWarps><<<grid, kMapWarps * 32, 0, st>>>(ml);
+    } else {
+        int grid = persistent_grid(map_kernel<4, kMapWarps>, kMapWarps * 32, 0, ctx->num_sms, items, kMapWarps);
+        map_kernel<4, kMapWarps><<<grid, kMapWarps * 32, 0, st>>>(ml);
+    }
+    MDG_CUDA_TRY(cudaGetLastError());
+    ctx->timings.n_launches++;
+    return MDG_OK;
+}
+
+int npl_for(int n_obs, int gw) {
+    int npl = (n_obs + gw - 1) / gw;
+    return npl <= 1 ? 1 : (npl <= 2 ? 2 : 4);
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdg_version(void) { return MDG_VERSION; }
+
+const char* mdg_last_error(void) { return g_error; }
+
+int mdg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void mdg_fit_config_default(mdg_fit_config* c) {
+    memset(c, 0, sizeof *c);
+    c->num_warmup = 500;
+    c->num_samples = 1000;
+    c->max_tree_depth = 10;
+    c->do_map = 1;
+    c->do_fwd_rev = 1;
+    c->find_heuristic_step_size = 1;
+    c->reference_quirks = 1;
+    c->pack_half_warps = 1;
+    c->target_accept = 0.8;
+    c->init_step_size = 1.0;
+    c->max_delta_energy = 1000.0;
+    c->init_radius = 2.0;
+    c->hpdi_prob = 0.68;
+    c->seed = 0;
+    c->q_prior_a = 2; c->q_prior_b = 3;
+    c->A_prior_a = 2; c->A_prior_b = 3;
+    c->c_prior_a = 1; c->c_prior_b = 9;
+    c->phi_prior_rate = 1.0 / 1000.0;
+    c->phi_min = 2.0;
+}
+
+int mdg_ctx_create(int device, mdg_ctx** out) {
+    if (!out) { set_error("mdg_ctx_create: out is NULL"); return MDG_ERR_INVALID; }
+    int n = mdg_device_count();
+    if (device < 0 || device >= n) {
+        set_error("mdg_ctx_create: device %d not available (%d CUDA devices visible)", device, n);
+        return MDG_ERR_CUDA;
+    }
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    MDG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("mdg_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                  prop.major, prop.minor);
+        return MDG_ERR_CUDA;
+    }
+    mdg_ctx* ctx = new mdg_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    MDG_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kNumEvents; ++i) MDG_CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
+    MDG_CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming));
+    *out = ctx;
+    return MDG_OK;
+}
+
+void mdg_ctx_destroy(mdg_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->buf) b.release();
+    for (int i = 0; i < kNumEvents; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+        if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int mdg_ctx_set_stream(mdg_ctx* ctx, void* cuda_stream) {
+    if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return MDG_OK;
+}
+
+int mdg_ctx_synchronize(mdg_ctx* ctx) {
+    if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
+    DeviceGuard guard(ctx->device);
+    MDG_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return MDG_OK;
+}
+
+int mdg_ctx_get_timings(mdg_ctx* ctx, mdg_timings* out) {
+    if (!ctx || !out) { set_error("ctx/out is NULL"); return MDG_ERR_INVALID; }
+    *out = ctx->timings;
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------
+int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_id, const uint32_t* n_alignments,
+                      const uint8_t* is_reverse, const uint8_t* pos0, const uint32_t* counts16,
+                      int64_t counts_stride, int fwd_ref, int fwd_obs, int rev_ref, int rev_obs, int max_position,
+                      uint32_t min_alignments, uint64_t min_y_sum, uint32_t* n_fwd_ref_row, uint32_t* n_rev_ref_row,
+                      float* f_fwd_row, float* f_rev_row, int8_t* z_row, uint64_t* y_sum_total_row,
+                      uint8_t* keep_row, int64_t* out_tax_id, uint32_t* out_n_alignments, int64_t* out_first_row,
+                      uint32_t* out_k, uint32_t* out_N, double* out_noise, int64_t* out_n_tax) {
+    if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
+    if (n_rows < 0 || !out_n_tax || max_position < 1 || max_position > MDG_MAX_POSITION || fwd_ref < 0 || fwd_ref > 3 ||
+        fwd_obs < 0 || fwd_obs > 3 || rev_ref < 0 || rev_ref > 3 || rev_obs < 0 || rev_obs > 3 ||
+        (mem != MDG_HOST && mem != MDG_DEVICE) || counts_stride < n_rows) {
+        set_error("mdg_counts_reduce: invalid argument");
+        return MDG_ERR_INVALID;
+    }
+    if (n_rows > 0 && (!tax_id || !n_alignments || !is_reverse || !pos0 || !counts16)) {
+        set_error("mdg_counts_reduce: NULL input column");
+        return MDG_ERR_INVALID;
+    }
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = ctx->stream;
+    ctx->timings = mdg_timings{};
+    *out_n_tax = 0;
+    if (n_rows == 0) return MDG_OK;
+    const int P = max_position, R = 2 * P;
+    const size_t n = (size_t)n_rows;
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+
+    // ---- stage inputs / outputs on the device for MDG_HOST ----
+    CountsLaunch cl = {};
+    const bool host = (mem == MDG_HOST);
+    struct OutCopy { void* host_ptr; const void* dev_ptr; size_t elem; bool per_tax; };
+    std::vector<OutCopy> copies;
+    if (host) {
+        // one arena for inputs, one for outputs
+        size_t in_bytes = n * (8 + 4 + 1 + 1) + 256 * 5 + 16 * ((n * 4 + 255) & ~(size_t)255);
+        int rc = ctx->buf[0].ensure(in_bytes);
+        if (rc) return rc;
+        unsigned char* base = ctx->buf[0].as<unsigned char>();
+        size_t off = 0;
+        auto put = [&](const void* src, size_t bytes) -> void* {
+            void* d = base + off;
+            cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+            off += (bytes + 255) & ~(size_t)255;
+            return d;
+        };
+        cl.tax_id = (const long long*)put(tax_id, n * 8);
+        cl.n_align = (const uint32_t*)put(n_alignments, n * 4);
+        cl.is_rev = (const uint8_t*)put(is_reverse, n);
+        cl.pos0 = (const uint8_t*)put(pos0, n);
+        const size_t col_stride = ((n * 4 + 255) & ~(size_t)255) / 4;
+        uint32_t* dcounts = (uint32_t*)(base + off);
+        for (int c = 0; c < 16; ++c)
+            cudaMemcpyAsync(dcounts + (size_t)c * col_stride, counts16 + (size_t)c * counts_stride, n * 4, cudaMemcpyHostToDevice, st);
+        cl.counts16 = dcounts;
+        cl.stride = (long long)col_stride;
+        MDG_CUDA_TRY(cudaGetLastError());
+        size_t out_bytes = n * (4 + 4 + 4 + 4 + 1 + 8 + 1 + 8 + 4 + 8) + n * (size_t)R * 8 + n * 24 + 256 * 16;
+        rc = ctx->buf[1].ensure(out_bytes);
+        if (rc) return rc;
+        unsigned char* ob = ctx->buf[1].as<unsigned char>();
+        size_t oo = 0;
+        auto take = [&](void* host_ptr, size_t elem, size_t count, bool per_tax) -> void* {
+            if (!host_ptr) return nullptr;
+            void* d = ob + oo;
+            oo += (elem * count + 255) & ~(size_t)255;
+            copies.push_back({host_ptr, d, elem, per_tax});
+            return d;
+        };
+        cl.n_fwd_row = (uint32_t*)take(n_fwd_ref_row, 4, n, false);
+        cl.n_rev_row = (uint32_t*)take(n_rev_ref_row, 4, n, false);
+        cl.f_fwd_row = (float*)take(f_fwd_row, 4, n, false);
+        cl.f_rev_row = (float*)take(f_rev_row, 4, n, false);
+        cl.z_row = (int8_t*)take(z_row, 1, n, false);
+        cl.y_row = (unsigned long long*)take(y_sum_total_row, 8, n, false);
+        cl.keep_row = (uint8_t*)take(keep_row, 1, n, false);
+        cl.out_tax = (long long*)take(out_tax_id, 8, n, true);
+        cl.out_nal = (uint32_t*)take(out_n_alignments, 4, n, true);
+        cl.out_first = (long long*)take(out_first_row, 8, n, true);
+        cl.out_k = (uint32_t*)take(out_k, 4 * (size_t)R, n, true);
+        cl.out_N = (uint32_t*)take(out_N, 4 * (size_t)R, n, true);
+        cl.out_noise = (double*)take(out_noise, 24, n, true);
+    } else {
+        cl.tax_id = (const long long*)tax_id; cl.n_align = n_alignments; cl.is_rev = is_reverse; cl.pos0 = pos0;
+        cl.counts16 = counts16; cl.stride = counts_stride;
+        cl.n_fwd_row = n_fwd_ref_row; cl.n_rev_row = n_rev_ref_row; cl.f_fwd_row = f_fwd_row; cl.f_rev_row = f_rev_row;
+        cl.z_row = z_row; cl.y_row = (unsigned long long*)y_sum_total_row; cl.keep_row = keep_row;
+        cl.out_tax = (long long*)out_tax_id; cl.out_nal = out_n_alignments; cl.out_first = (long long*)out_first_row;
+        cl.out_k = out_k; cl.out_N = out_N; cl.out_noise = out_noise;
+    }
+    cl.n_rows = n_rows;
+    cl.fwd_ref = fwd_ref; cl.fwd_obs = fwd_obs; cl.rev_ref = rev_ref; cl.rev_obs = rev_obs;
+    cl.P = P; cl.min_align = min_alignments; cl.min_y = min_y_sum;
+    // staged columns: the reference-base rows of the two substitutions (+ all off-diagonals for noise)
+    bool need[16] = {};
+    for (int o = 0; o < 4; ++o) { need[fwd_ref * 4 + o] = true; need[rev_ref * 4 + o] = true; }
+    if (cl.out_noise) for (int r = 0; r < 4; ++r) for (int o = 0; o < 4; ++o) if (r != o) need[r * 4 + o] = true;
+    cl.ncols = 0;
+    for (int c = 0; c < 16; ++c) {
+        cl.col_slot[c] = -1;
+        if (need[c]) { cl.col_slot[c] = cl.ncols; cl.col_id[cl.ncols++] = c; }
+    }
+    auto aligned16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+    cl.use_tma = aligned16(cl.tax_id) && aligned16(cl.n_align) && aligned16(cl.is_rev) && aligned16(cl.pos0) &&
+                 aligned16(cl.counts16) && (cl.stride % 4 == 0);
+
+    // ---- tiling ladder: widen the lookahead if a TaxID does not fit ----
+    static const int ladder_T[3] = {1024, 1024, 512};
+    static const int ladder_L[3] = {128, 512, MDG_MAX_SEGMENT_ROWS};
+    int rc = ctx->buf[2].ensure(64);
+    if (rc) return rc;
+    long long* d_ntax = ctx->buf[2].as<long long>();
+    int* d_err = reinterpret_cast<int*>(d_ntax + 1);
+    unsigned int* d_ticket = reinterpret_cast<unsigned int*>(d_ntax + 2);
+    int h_err = 0;
+    long long h_ntax = 0;
+    for (int step = 0; step < 3; ++step) {
+        cl.T = ladder_T[step];
+        cl.L = ladder_L[step];
+        const int cap = cl.T + cl.L;
+        const size_t smem = (size_t)8 * (cap + 2) + (size_t)4 * cl.ncols * cap + (size_t)4 * cap + (size_t)4 * (cap + 4) +
+                            (size_t)3 * cap + (size_t)kCountsWarps * 2 * R * 4 + 64;
+        if (smem > 227 * 1024) { set_error("mdg_counts_reduce: tile does not fit shared memory"); return MDG_ERR_SEGMENT_TOO_LONG; }
+        const long long n_tiles = (n_rows + cl.T - 1) / cl.T;
+        rc = ctx->buf[3].ensure((size_t)n_tiles * 8);
+        if (rc) return rc;
+        cl.tile_state = ctx->buf[3].as<unsigned long long>();
+        cl.tile_ticket = d_ticket;
+        cl.n_tax_out = d_ntax;
+        cl.error_flag = d_err;
+        MDG_CUDA_TRY(cudaMemsetAsync(d_ntax, 0, 64, st));
+        MDG_CUDA_TRY(cudaMemsetAsync(cl.tile_state, 0, (size_t)n_tiles * 8, st));
+        MDG_CUDA_TRY(cudaFuncSetAttribute(counts_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+        counts_reduce_kernel<<<(unsigned)n_tiles, kCountsThreads, smem, st>>>(cl);
+        MDG_CUDA_TRY(cudaGetLastError());
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+        ctx->timings.n_launches++;
+        MDG_CUDA_TRY(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MDG_CUDA_TRY(cudaMemcpyAsync(&h_ntax, d_ntax, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        MDG_CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_err != CE_SEGMENT_TOO_LONG) break;
+    }
+    if (h_err == CE_SEGMENT_TOO_LONG) {
+        set_error("mdg_counts_reduce: a TaxID has more than %d rows (rows must be grouped by tax_id)", MDG_MAX_SEGMENT_ROWS);
+        return MDG_ERR_SEGMENT_TOO_LONG;
+    }
+    if (h_err == CE_OVERFLOW) {
+        set_error("mdg_counts_reduce: a reference-base row sum exceeds uint32 (utils.py:338-339)");
+        return MDG_ERR_OVERFLOW;
+    }
+    *out_n_tax = h_ntax;
+    if (host) {
+        for (const auto& c : copies) {
+            size_t count = c.per_tax ? (size_t)h_ntax : n;
+            if (count) MDG_CUDA_TRY(cudaMemcpyAsync(c.host_ptr, c.dev_ptr, c.elem * count, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+    MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->timings.counts_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+    ctx->timings.total_ms = elapsed(ctx->ev[0], ctx->ev[3]);
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3-K7
+// ---------------------------------------------------------------------------------------------
+int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const int64_t* tax_id, const uint32_t* k,
+                  const uint32_t* N, const uint32_t* mism12, const double* noise3, const mdg_fit_config* cfg,
+                  mdg_fit_result* out, float* out_median, float* out_hpdi_lo, float* out_hpdi_hi,
+                  double* out_samples, double* out_trace, double* out_waic) {
+    if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
+    if (!cfg || n_tax < 0 || max_position < 1 || max_position > MDG_MAX_POSITION || (mem != MDG_HOST && mem != MDG_DEVICE)) {
+        set_error("mdg_fit_batch: invalid argument");
+        return MDG_ERR_INVALID;
+    }
+    if (cfg->num_samples < 1 || cfg->num_samples > 4096 || cfg->num_warmup < 0 || cfg->max_tree_depth < 1 ||
+        cfg->max_tree_depth > kMaxTreeDepth) {
+        set_error("mdg_fit_batch: need 1 <= num_samples <= 4096, num_warmup >= 0, 1 <= max_tree_depth <= %d", kMaxTreeDepth);
+        return MDG_ERR_INVALID;
+    }
+    if (n_tax > 0 && (!tax_id || !k || !N || !out)) { set_error("mdg_fit_batch: NULL tax_id/k/N/out"); return MDG_ERR_INVALID; }
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = ctx->stream;
+    ctx->timings = mdg_timings{};
+    if (n_tax == 0) return MDG_OK;
+    const int P = max_position, R = 2 * P, S = cfg->num_samples, W = cfg->num_warmup;
+    const bool host = (mem == MDG_HOST);
+    const bool fwd_rev = cfg->do_fwd_rev != 0;
+    const bool pack = fwd_rev && cfg->pack_half_warps && P <= 16;
+    const Priors pr = make_priors(*cfg);
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+
+    const long long chunk_cap = 16384;
+    const long long chunk_max = std::min<long long>(n_tax, chunk_cap);
+    const int sample_runs = out_samples ? MDG_NUM_RUNS : (fwd_rev ? 3 : 1);
+    const int items_per_tax = R + (fwd_rev ? 2 : 0);
+
+    // ---- device buffers ----
+    // persistent scratch (per chunk)
+    int rc;
+    if ((rc = ctx->buf[4].ensure((size_t)chunk_max * MDG_NUM_RUNS * sizeof(RunRecord)))) return rc;
+    if ((rc = ctx->buf[5].ensure((size_t)chunk_max * 2 * sizeof(MapRecord)))) return rc;
+    if ((rc = ctx->buf[6].ensure((size_t)chunk_max * items_per_tax * 3 * sizeof(double)))) return rc;
+    if ((rc = ctx->buf[7].ensure(256))) return rc;  // work counters + leapfrog totals
+    if (!out_samples && (rc = ctx->buf[8].ensure((size_t)chunk_max * sample_runs * S * 4 * sizeof(double)))) return rc;
+    if (!out_waic && (rc = ctx->buf[9].ensure((size_t)chunk_max * MDG_NUM_RUNS * 2 * R * sizeof(double)))) return rc;
+    // staged inputs / outputs for MDG_HOST (whole batch)
+    const int64_t* d_tax = tax_id; const uint32_t* d_k = k; const uint32_t* d_N = N; const uint32_t* d_m12 = mism12;
+    const double* d_noise = noise3;
+    mdg_fit_result* d_out = out; float* d_med = out_median; float* d_lo = out_hpdi_lo; float* d_hi = out_hpdi_hi;
+    double* d_samples = out_samples; double* d_trace = out_trace; double* d_waic_user = out_waic;
+    const size_t nt = (size_t)n_tax;
+    if (host) {
+        if ((rc = ctx->buf[10].ensure(nt * 8))) return rc;
+        if ((rc = ctx->buf[11].ensure(nt * R * 4))) return rc;
+        if ((rc = ctx->buf[12].ensure(nt * R * 4))) return rc;
+        MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[10].ptr, tax_id, nt * 8, cudaMemcpyHostToDevice, st));
+        MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[11].ptr, k, nt * R * 4, cudaMemcpyHostToDevice, st));
+        MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[12].ptr, N, nt * R * 4, cudaMemcpyHostToDevice, st));
+        d_tax = ctx->buf[10].as<int64_t>(); d_k = ctx->buf[11].as<uint32_t>(); d_N = ctx->buf[12].as<uint32_t>();
+        if (mism12) {
+            if ((rc = ctx->buf[13].ensure(nt * R * 12 * 4))) return rc;
+            MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[13].ptr, mism12, nt * R * 12 * 4, cudaMemcpyHostToDevice, st));
+            d_m12 = ctx->buf[13].as<uint32_t>();
+        }
+        if (noise3) {
+            if ((rc = ctx->buf[14].ensure(nt * 24))) return rc;
+            MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[14].ptr, noise3, nt * 24, cudaMemcpyHostToDevice, st));
+            d_noise = ctx->buf[14].as<double>();
+        }
+        if ((rc = ctx->buf[15].ensure(nt * sizeof(mdg_fit_result)))) return rc;
+        d_out = ctx->buf[15].as<mdg_fit_result>();
+        if ((rc = ctx->buf[16].ensure(nt * R * 4 * 3))) return rc;
+        d_med = ctx->buf[16].as<float>(); d_lo = d_med + nt * R; d_hi = d_lo + nt * R;
+        if (out_samples) {
+            if ((rc = ctx->buf[17].ensure(nt * MDG_NUM_RUNS * S * 4 * 8))) return rc;
+            d_samples = ctx->buf[17].as<double>();
+        }
+        if (out_trace) {
+            if ((rc = ctx->buf[18].ensure(nt * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8))) return rc;
+            d_trace = ctx->buf[18].as<double>();
+        }
+        if (out_waic) {
+            if ((rc = ctx->buf[19].ensure(nt * MDG_NUM_RUNS * 2 * R * 8))) return rc;
+            d_waic_user = ctx->buf[19].as<double>();
+        }
+    } else {
+        if (!d_med || !d_lo || !d_hi) {
+            if ((rc = ctx->buf[16].ensure(nt * R * 4 * 3))) return rc;
+            float* base = ctx->buf[16].as<float>();
+            if (!d_med) d_med = base;
+            if (!d_lo) d_lo = base + nt * R;
+            if (!d_hi) d_hi = base + 2 * nt * R;
+        }
+    }
+    if (d_trace) MDG_CUDA_TRY(cudaMemsetAsync(d_trace, 0xFF, nt * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8, st));
+    if (out_samples) MDG_CUDA_TRY(cudaMemsetAsync(d_samples, 0xFF, nt * MDG_NUM_RUNS * (size_t)S * 4 * 8, st));
+
+    unsigned int* d_counters = ctx->buf[7].as<unsigned int>();                       // [8]
+    unsigned long long* d_leap = reinterpret_cast<unsigned long long*>(d_counters + 16);  // [6]
+    MDG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 256, st));
+
+    float map_ms = 0, nuts_ms = 0, ppc_ms = 0, asm_ms = 0;
+    for (long long c0 = 0; c0 < n_tax; c0 += chunk_cap) {
+        const int nc = (int)std::min<long long>(chunk_cap, n_tax - c0);
+        RunRecord* d_rec = ctx->buf[4].as<RunRecord>();
+        MapRecord* d_map = ctx->buf[5].as<MapRecord>();
+        double* d_pred = ctx->buf[6].as<double>();
+        double* d_waic = d_waic_user ? d_waic_user + (size_t)c0 * MDG_NUM_RUNS * 2 * R : ctx->buf[9].as<double>();
+        double* d_smp = out_samples ? d_samples + (size_t)c0 * MDG_NUM_RUNS * S * 4 : ctx->buf[8].as<double>();
+        MDG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 64, st));
+        MDG_CUDA_TRY(cudaMemsetAsync(d_waic, 0, (size_t)nc * MDG_NUM_RUNS * 2 * R * 8, st));
+        MDG_CUDA_TRY(cudaMemsetAsync(d_rec, 0, (size_t)nc * MDG_NUM_RUNS * sizeof(RunRecord), st));
+
+        // ---- K3 MAP ----
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+        if (cfg->do_map) {
+            MapLaunch ml = {};
+            ml.tax_id = d_tax + c0; ml.k = d_k + (size_t)c0 * R; ml.N = d_N + (size_t)c0 * R;
+            ml.n_tax = nc; ml.P = P; ml.pr = pr; ml.work_counter = d_counters + 0; ml.rec = d_map;
+            if ((rc = launch_map(ctx, st, ml, npl_for(R, 32)))) return rc;
+        }
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
+
+        // ---- K4 NUTS: four launches on four streams (they share the SMs as CTAs retire) ----
+        FitLaunch fl = {};
+        fl.tax_id = d_tax + c0; fl.k = d_k + (size_t)c0 * R; fl.N = d_N + (size_t)c0 * R;
+        fl.n_tax = nc; fl.P = P; fl.cfg = *cfg; fl.pr = pr;
+        fl.n_windows = adaptation_window_ends(W, fl.win_end);
+        fl.rec = d_rec; fl.waic = d_waic; fl.samples = d_smp; fl.sample_runs = sample_runs;
+        fl.trace = d_trace ? d_trace + (size_t)c0 * MDG_NUM_RUNS * (W + S) * 4 : nullptr;
+        for (int r = 0; r < MDG_NUM_RUNS; ++r) fl.sample_slot[r] = out_samples ? r : ((r & 1) ? -1 : r / 2);
+        MDG_CUDA_TRY(cudaEventRecord(ctx->fork_ev, st));
+        for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0));
+        {
+            FitLaunch a = fl;  // PMD, all positions
+            a.n_masks = 1; a.mask0 = 0; a.n_items = nc; a.work_counter = d_counters + 1;
+            if ((rc = launch_nuts_dispatch<0>(ctx, st, a, npl_for(R, 32), 32))) return rc;
+            FitLaunch b = fl;  // null, all positions
+            b.n_masks = 1; b.mask0 = 0; b.n_items = nc; b.work_counter = d_counters + 2;
+            if ((rc = launch_nuts_dispatch<1>(ctx, ctx->side[0], b, npl_for(R, 32), 32))) return rc;
+            if (fwd_rev) {
+                FitLaunch c = fl, d = fl;
+                c.work_counter = d_counters + 3; d.work_counter = d_counters + 4;
+                if (pack) {
+                    c.n_items = nc; d.n_items = nc; c.n_masks = 1; d.n_masks = 1; c.mask0 = 1; d.mask0 = 1;
+                    if ((rc = launch_nuts_dispatch<0>(ctx, ctx->side[1], c, 1, 16))) return rc;
+                    if ((rc = launch_nuts_dispatch<1>(ctx, ctx->side[2], d, 1, 16))) return rc;
+                } else {
+                    c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_masks = 2; d.n_masks = 2; c.mask0 = 1; d.mask0 = 1;
+                    if ((rc = launch_nuts_dispatch<0>(ctx, ctx->side[1], c, npl_for(P, 32), 32))) return rc;
+                    if ((rc = launch_nuts_dispatch<1>(ctx, ctx->side[2], d, npl_for(P, 32), 32))) return rc;
+                }
+            }
+        }
+        for (int i = 0; i < 3; ++i) {
+            MDG_CUDA_TRY(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
+            MDG_CUDA_TRY(cudaStreamWaitEvent(st, ctx->join_ev[i], 0));
+        }
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[6], st));
+
+        // ---- K6 posterior predictive ----
+        {
+            PpcLaunch pl = {};
+            pl.tax_id = d_tax + c0; pl.N = d_N + (size_t)c0 * R; pl.n_tax = nc; pl.P = P; pl.cfg = *cfg; pl.pr = pr;
+            pl.samples = d_smp; pl.sample_runs = sample_runs;
+            for (int r = 0; r < MDG_NUM_RUNS; ++r) pl.sample_slot[r] = fl.sample_slot[r];
+            pl.rec = d_rec; pl.work_counter = d_counters + 5; pl.items_per_tax = items_per_tax;
+            int sp = 64;
+            while (sp < S) sp <<= 1;
+            pl.s_pad = sp;
+            pl.pred = d_pred;
+            const size_t smem = (size_t)kPpcWarps * sp * 4;
+            MDG_CUDA_TRY(cudaFuncSetAttribute(ppc_kernel<kPpcWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = persistent_grid(ppc_kernel<kPpcWarps>, kPpcWarps * 32, smem, ctx->num_sms, (long long)nc * items_per_tax, kPpcWarps);
+            ppc_kernel<kPpcWarps><<<grid, kPpcWarps * 32, smem, st>>>(pl);
+            MDG_CUDA_TRY(cudaGetLastError());
+            ctx->timings.n_launches++;
+        }
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[7], st));
+
+        // ---- K5/K7 assembly ----
+        {
+            AssembleLaunch al = {};
+            al.tax_id = d_tax + c0; al.k = d_k + (size_t)c0 * R; al.N = d_N + (size_t)c0 * R;
+            al.mism12 = d_m12 ? d_m12 + (size_t)c0 * R * 12 : nullptr;
+            al.noise3 = d_noise ? d_noise + (size_t)c0 * 3 : nullptr;
+            al.n_tax = nc; al.P = P; al.cfg = *cfg; al.rec = d_rec; al.map = cfg->do_map ? d_map : nullptr;
+            al.waic = d_waic; al.pred = d_pred; al.items_per_tax = items_per_tax;
+            al.out = d_out + c0; al.out_median = d_med + (size_t)c0 * R; al.out_lo = d_lo + (size_t)c0 * R;
+            al.out_hi = d_hi + (size_t)c0 * R; al.leapfrog_totals = d_leap;
+            assemble_kernel<<<(nc + 127) / 128, 128, 0, st>>>(al);
+            MDG_CUDA_TRY(cudaGetLastError());
+            ctx->timings.n_launches++;
+        }
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[8], st));
+        // per-chunk timing needs the events to have completed; chunks are seconds long, so the
+        // sync costs nothing measurable
+        MDG_CUDA_TRY(cudaStreamSynchronize(st));
+        map_ms += elapsed(ctx->ev[4], ctx->ev[5]);
+        nuts_ms += elapsed(ctx->ev[5], ctx->ev[6]);
+        ppc_ms += elapsed(ctx->ev[6], ctx->ev[7]);
+        asm_ms += elapsed(ctx->ev[7], ctx->ev[8]);
+    }
+
+    if (host) {
+        MDG_CUDA_TRY(cudaMemcpyAsync(out, d_out, nt * sizeof(mdg_fit_result), cudaMemcpyDeviceToHost, st));
+        if (out_median) MDG_CUDA_TRY(cudaMemcpyAsync(out_median, d_med, nt * R * 4, cudaMemcpyDeviceToHost, st));
+        if (out_hpdi_lo) MDG_CUDA_TRY(cudaMemcpyAsync(out_hpdi_lo, d_lo, nt * R * 4, cudaMemcpyDeviceToHost, st));
+        if (out_hpdi_hi) MDG_CUDA_TRY(cudaMemcpyAsync(out_hpdi_hi, d_hi, nt * R * 4, cudaMemcpyDeviceToHost, st));
+        if (out_samples) MDG_CUDA_TRY(cudaMemcpyAsync(out_samples, d_samples, nt * MDG_NUM_RUNS * S * 4 * 8, cudaMemcpyDeviceToHost, st));
+        if (out_trace) MDG_CUDA_TRY(cudaMemcpyAsync(out_trace, d_trace, nt * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8, cudaMemcpyDeviceToHost, st));
+        if (out_waic) MDG_CUDA_TRY(cudaMemcpyAsync(out_waic, d_waic_user, nt * MDG_NUM_RUNS * 2 * R * 8, cudaMemcpyDeviceToHost, st));
+    }
+    unsigned long long h_leap[MDG_NUM_RUNS] = {};
+    MDG_CUDA_TRY(cudaMemcpyAsync(h_leap, d_leap, sizeof h_leap, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[9], st));
+    MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->timings.map_ms = map_ms;
+    ctx->timings.nuts_ms = nuts_ms;
+    ctx->timings.ppc_ms = ppc_ms;
+    ctx->timings.assemble_ms = asm_ms;
+    ctx->timings.total_ms = elapsed(ctx->ev[0], ctx->ev[9]);
+    for (int r = 0; r < MDG_NUM_RUNS; ++r) ctx->timings.leapfrogs[r] = h_leap[r];
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// test / measurement entry points
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+__global__ void test_lgam_kernel(long long n, const double* x, double* lg, double* dg) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) {
+        double a, b;
+        lgam_digam(x[i], a, b);
+        lg[i] = a;
+        dg[i] = b;
+    }
+}
+
+__global__ void test_philox_kernel(long long n, const uint32_t* key2, const uint32_t* ctr4, uint32_t* out4) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint4 o = philox4x32(make_uint2(key2[2 * i], key2[2 * i + 1]), ctr4[4 * i], ctr4[4 * i + 1], ctr4[4 * i + 2], ctr4[4 * i + 3]);
+        out4[4 * i] = o.x; out4[4 * i + 1] = o.y; out4[4 * i + 2] = o.z; out4[4 * i + 3] = o.w;
+    }
+}
+
+template <int MODEL, int NPL>
+__global__ void test_logp_kernel(int P, const uint32_t* k, const uint32_t* N, Priors pr, int mask, int jac,
+                                 long long n_eval, const double* u, double* out_logp, double* out_grad, double* out_ll) {
+    constexpr int D = ModelDim<MODEL>::value;
+    const int lane = threadIdx.x & 31;
+    const long long e = blockIdx.x;
+    if (e >= n_eval) return;
+    LaneObs<NPL> ob;
+    load_obs<NPL, 32>(ob, k, N, P, mask, lane);
+    double logC[NPL];
+    log_binom_coeff<NPL>(ob, logC);
+    const int n_obs = mask == 0 ? 2 * P : P;
+    double uu[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) uu[j] = u[e * 4 + j];
+    double logp, grad[D], ll[NPL];
+    bool valid;
+    eval_model<MODEL, NPL, 32>(ob, uu, jac, pr, n_obs < NPL * 32, 0xffffffffu, lane, logp, grad, ll, valid);
+    double sumC = 0.0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) sumC += logC[s];
+    sumC = group_sum<32>(sumC, 0xffffffffu);
+    if (lane == 0) {
+        out_logp[e] = valid ? logp + sumC : nan("");
+        for (int j = 0; j < 4; ++j) out_grad[e * 4 + j] = j < D ? grad[j] : 0.0;
+    }
+    if (out_ll) {
+#pragma unroll
+        for (int s = 0; s < NPL; ++s)
+            if (ob.act[s]) out_ll[e * 2 * P + (mask == 2 ? P : 0) + s * 32 + lane] = ll[s] + logC[s];
+    }
+}
+
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdg_test_lgamma_digamma(mdg_ctx* ctx, int64_t n, const double* x, double* out_lgamma, double* out_digamma) {
+    if (!ctx || n < 0) { set_error("invalid argument"); return MDG_ERR_INVALID; }
+    if (n == 0) return MDG_OK;
+    DeviceGuard guard(ctx->device);
+    int rc = ctx->buf[20].ensure((size_t)n * 24);
+    if (rc) return rc;
+    double* d = ctx->buf[20].as<double>();
+    MDG_CUDA_TRY(cudaMemcpyAsync(d, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    test_lgam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, d, d + n, d + 2 * n);
+    MDG_CUDA_TRY(cudaGetLastError());
+    MDG_CUDA_TRY(cudaMemcpyAsync(out_lgamma, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MDG_CUDA_TRY(cudaMemcpyAsync(out_digamma, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MDG_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return MDG_OK;
+}
+
+int mdg_test_philox(mdg_ctx* ctx, int64_t n, const uint32_t* key2, const uint32_t* ctr4, uint32_t* out4) {
+    if (!ctx || n < 0) { set_error("invalid argument"); return MDG_ERR_INVALID; }
+    if (n == 0) return MDG_OK;
+    DeviceGuard guard(ctx->device);
+    int rc = ctx->buf[20].ensure((size_t)n * 40);
+    if (rc) return rc;
+    uint32_t* d = ctx->buf[20].as<uint32_t>();
+    MDG_CUDA_TRY(cudaMemcpyAsync(d, key2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MDG_CUDA_TRY(cudaMemcpyAsync(d + 2 * n, ctr4, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    test_philox_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, d, d + 2 * n, d + 6 * n);
+    MDG_CUDA_TRY(cudaGetLastError());
+    MDG_CUDA_TRY(cudaMemcpyAsync(out4, d + 6 * n, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    MDG_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return MDG_OK;
+}
+
+int mdg_test_logp_grad(mdg_ctx* ctx, int max_position, const uint32_t* k, const uint32_t* N, const mdg_fit_config* cfg,
+                       int model, int lane_mask, int with_jacobian, int64_t n_eval, const double* u, double* out_logp,
+                       double* out_grad, double* out_ll) {
+    if (!ctx || !cfg || max_position < 1 || max_position > MDG_MAX_POSITION || n_eval < 0 || model < 0 || model > 1 ||
+        lane_mask < 0 || lane_mask > 2) {
+        set_error("invalid argument");
+        return MDG_ERR_INVALID;
+    }
+    if (n_eval == 0) return MDG_OK;
+    DeviceGuard guard(ctx->device);
+    const int P = max_position, R = 2 * P;
+    const size_t ne = (size_t)n_eval;
+    int rc = ctx->buf[20].ensure((size_t)R * 8 + ne * (32 + 8 + 32 + (size_t)R * 8) + 1024);
+    if (rc) return rc;
+    unsigned char* base = ctx->buf[20].as<unsigned char>();
+    uint32_t* dk = (uint32_t*)base;
+    uint32_t* dN = dk + R;
+    double* du = (double*)(base + (((size_t)R * 8 + 255) & ~(size_t)255));
+    double* dlogp = du + ne * 4;
+    double* dgrad = dlogp + ne;
+    double* dll = dgrad + ne * 4;
+    cudaStream_t st = ctx->stream;
+    MDG_CUDA_TRY(cudaMemcpyAsync(dk, k, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+    MDG_CUDA_TRY(cudaMemcpyAsync(dN, N, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+    MDG_CUDA_TRY(cudaMemcpyAsync(du, u, ne * 32, cudaMemcpyHostToDevice, st));
+    MDG_CUDA_TRY(cudaMemsetAsync(dll, 0, ne * R * 8, st));
+    const Priors pr = make_priors(*cfg);
+    const int n_obs = lane_mask == 0 ? R : P;
+    const int npl = npl_for(n_obs, 32);
+    const unsigned grid = (unsigned)n_eval;
+#define MDG_LAUNCH_LOGP(M, NPL_) test_logp_kernel<M, NPL_><<<grid, 32, 0, st>>>(P, dk, dN, pr, lane_mask, with_jacobian, n_eval, du, dlogp, dgrad, out_ll ? dll : nullptr)
+    if (model == 0) { if (npl == 1) MDG_LAUNCH_LOGP(0, 1); else if (npl == 2) MDG_LAUNCH_LOGP(0, 2); else MDG_LAUNCH_LOGP(0, 4); }
+    else { if (npl == 1) MDG_LAUNCH_LOGP(1, 1); else if (npl == 2) MDG_LAUNCH_LOGP(1, 2); else MDG_LAUNCH_LOGP(1, 4); }
+#undef MDG_LAUNCH_LOGP
+    MDG_CUDA_TRY(cudaGetLastError());
+    MDG_CUDA_TRY(cudaMemcpyAsync(out_logp, dlogp, ne * 8, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaMemcpyAsync(out_grad, dgrad, ne * 32, cudaMemcpyDeviceToHost, st));
+    if (out_ll) MDG_CUDA_TRY(cudaMemcpyAsync(out_ll, dll, ne * R * 8, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    return MDG_OK;
+}
+
+int mdg_measure_fp64_peak(mdg_ctx* ctx, double* out_tflops) {
+    if (!ctx || !out_tflops) { set_error("invalid argument"); return MDG_ERR_INVALID; }
+    DeviceGuard guard(ctx->device);
+    int rc = ctx->buf[20].ensure(64);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const int iters = 20000, threads = 512, blocks = ctx->num_sms * 4;
+    fp64_peak_kernel<<<blocks, threads, 0, st>>>(ctx->buf[20].as<double>(), 1000);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[10], st));
+        fp64_peak_kernel<<<blocks, threads, 0, st>>>(ctx->buf[20].as<double>(), iters);
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[11], st));
+        MDG_CUDA_TRY(cudaStreamSynchronize(st));
+        MDG_CUDA_TRY(cudaGetLastError());
+        const double ms = elapsed(ctx->ev[10], ctx->ev[11]);
+        const double flops = 2.0 * 8.0 * iters * (double)threads * blocks;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *out_tflops = best;
+    return MDG_OK;
+}
+
+}  // extern "C"

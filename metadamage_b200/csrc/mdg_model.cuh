@@ -1,0 +1,209 @@
+// mdg_model.cuh — K2: beta-binomial log-joint and analytic gradient, one lane per position.
+//
+// Follows fits.py:43-59 (model_PMD) and fits.py:62-67 (model_null) with numpyro 0.4.1's
+// BetaBinomial.log_prob and the sigmoid / exp bijections of its unconstrained parameterisation
+// (SURVEY.md 8c-notes). A GW-wide lane group (32 = a warp, 16 = half a warp) owns one chain;
+// lane `lig` holds NPL positions; sums go through __shfl_xor_sync butterflies so that every
+// lane of the group ends with bit-identical values and all control flow stays group-uniform.
+#pragma once
+#include "mdg_common.cuh"
+
+namespace mdg {
+
+struct Priors {
+    double qa, qb, Aa, Ab, ca, cb;  // Beta priors (fits.py:46-48, 63)
+    double rate, phi_min;           // Exponential(rate) on delta = phi - phi_min (fits.py:53-54)
+    double nlb_q, nlb_A, nlb_c;     // -log B(a,b) of the three Beta priors
+    double log_rate;
+};
+
+template <int MODEL>
+struct ModelDim { static constexpr int value = MODEL == 0 ? 4 : 2; };
+
+// per-lane observations; inactive slots carry k = N = 0 (their terms are masked out of the sums,
+// and the group's spare slot is what evaluates the position-independent lgamma(phi) for free)
+template <int NPL>
+struct LaneObs {
+    double k[NPL], N[NPL], x[NPL];
+    bool act[NPL];
+};
+
+template <int NPL, int GW>
+__device__ __forceinline__ void load_obs(LaneObs<NPL>& ob, const uint32_t* __restrict__ k,
+                                         const uint32_t* __restrict__ N, int P, int mask, int lig) {
+    const int n_obs = mask == 0 ? 2 * P : P;
+    const int base = mask == 2 ? P : 0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        int i = s * GW + lig;
+        bool a = i < n_obs;
+        int dense = base + (a ? i : 0);
+        ob.act[s] = a;
+        ob.k[s] = a ? (double)__ldg(k + dense) : 0.0;
+        ob.N[s] = a ? (double)__ldg(N + dense) : 0.0;
+        ob.x[s] = a ? (double)(dense < P ? dense : dense - P) : 0.0;
+    }
+}
+
+// log C(N,k): the parameter-free part of BetaBinomial.log_prob
+template <int NPL>
+__device__ __forceinline__ void log_binom_coeff(const LaneObs<NPL>& ob, double (&logC)[NPL]) {
+#pragma unroll
+    for (int s = 0; s < NPL; ++s)
+        logC[s] = ob.act[s] ? lgam(ob.N[s] + 1.0) - lgam(ob.k[s] + 1.0) - lgam(ob.N[s] - ob.k[s] + 1.0) : 0.0;
+}
+
+// Evaluate log p(y | theta(u)) + log prior(theta(u)) [+ log |d theta / d u| if jac] and its
+// gradient w.r.t. u, for the group's chain. `ll[s]` is the per-position log-likelihood WITHOUT
+// log C(N,k). `valid` is false where the reference would produce NaN (clip(Dz,0,1) reaching 1,
+// fits.py:50) or anything is non-finite. `has_spare`: the group's last slot is inactive.
+template <int MODEL, int NPL, int GW>
+__device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double (&u)[ModelDim<MODEL>::value],
+                                           int jac, const Priors& pr, bool has_spare, unsigned gmask, int lig,
+                                           double& logp, double (&grad)[ModelDim<MODEL>::value],
+                                           double (&ll)[NPL], bool& valid) {
+    constexpr int D = ModelDim<MODEL>::value;
+    const double dj = (double)jac;
+
+    // --- group-uniform transforms, one parameter per lane, then broadcast --------------------
+    double myu = u[0];
+#pragma unroll
+    for (int j = 1; j < D; ++j) myu = (lig == j) ? u[j] : myu;
+    double e = exp(-fabs(myu));
+    double l1p = log1p(e);
+    double inv = 1.0 / (1.0 + e);
+    double sp = fmax(myu, 0.0) + l1p;             // softplus(u)
+    double sg = (myu >= 0.0) ? inv : e * inv;     // sigmoid(u)
+    double ex = (myu >= 0.0) ? 1.0 / e : e;       // exp(u)
+    // this lane's prior (+ Jacobian) term of the log density
+    double lp_lane = 0.0;
+    {
+        double a = pr.qa, b = pr.qb, nlb = pr.nlb_q;
+        if (MODEL == 0) {
+            if (lig == 1) { a = pr.Aa; b = pr.Ab; nlb = pr.nlb_A; }
+            if (lig == 2) { a = pr.ca; b = pr.cb; nlb = pr.nlb_c; }
+        }
+        double beta_term = (a - 1.0 + dj) * (myu - sp) + (b - 1.0 + dj) * (-sp) + nlb;
+        double exp_term = pr.log_rate - pr.rate * ex + dj * myu;
+        lp_lane = (lig < D - 1) ? beta_term : (lig == D - 1 ? exp_term : 0.0);
+    }
+    const double q = __shfl_sync(gmask, sg, 0, GW);
+    const double log1mq = -__shfl_sync(gmask, sp, 0, GW);
+    const double delta = __shfl_sync(gmask, ex, D - 1, GW);
+    double A = 0.0, c = 0.0;
+    if (MODEL == 0) {
+        A = __shfl_sync(gmask, sg, 1, GW);
+        c = __shfl_sync(gmask, sg, 2, GW);
+    }
+    const double phi = delta + pr.phi_min;
+
+    // --- per-position special functions -------------------------------------------------------
+    double lg1[NPL], lg2[NPL], lg3[NPL], dg1[NPL], dg2[NPL], dg3[NPL];
+    double lga[NPL], lgb[NPL], dga[NPL], dgb[NPL], Dz[NPL], w[NPL];
+    bool bad = false;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        w[s] = (MODEL == 0) ? exp(ob.x[s] * log1mq) : 1.0;
+        double Dv = (MODEL == 0) ? fma(A, w[s], c) : q;
+        bool ok = (Dv > 0.0) && (Dv < 1.0);
+        bad |= (!ok) && ob.act[s];
+        Dv = ok ? Dv : 0.5;
+        Dz[s] = Dv;
+        double al = Dv * phi, be = (1.0 - Dv) * phi;
+        lgam_digam(ob.k[s] + al, lg1[s], dg1[s]);
+        lgam_digam(ob.N[s] - ob.k[s] + be, lg2[s], dg2[s]);
+        lgam_digam(ob.N[s] + phi, lg3[s], dg3[s]);
+        if (MODEL == 0) {
+            lgam_digam(al, lga[s], dga[s]);
+            lgam_digam(be, lgb[s], dgb[s]);
+        }
+    }
+    // position-independent pieces: the spare slot (k = N = 0) has just evaluated them
+    double lgphi, dgphi;
+    if (has_spare) {
+        lgphi = __shfl_sync(gmask, lg3[NPL - 1], GW - 1, GW);
+        dgphi = __shfl_sync(gmask, dg3[NPL - 1], GW - 1, GW);
+    } else {
+        lgam_digam(phi, lgphi, dgphi);
+    }
+    if (MODEL == 1) {
+        double ua, da_, ub, db_;
+        if (has_spare) {
+            ua = __shfl_sync(gmask, lg1[NPL - 1], GW - 1, GW);
+            da_ = __shfl_sync(gmask, dg1[NPL - 1], GW - 1, GW);
+            ub = __shfl_sync(gmask, lg2[NPL - 1], GW - 1, GW);
+            db_ = __shfl_sync(gmask, dg2[NPL - 1], GW - 1, GW);
+        } else {
+            lgam_digam(q * phi, ua, da_);
+            lgam_digam((1.0 - q) * phi, ub, db_);
+        }
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) { lga[s] = ua; dga[s] = da_; lgb[s] = ub; dgb[s] = db_; }
+    }
+
+    // --- per-lane partial sums ------------------------------------------------------------------
+    double s_ll = lp_lane, s_dD = 0.0, s_dDw = 0.0, s_dDxw = 0.0, s_dphi = 0.0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        double lls = lg1[s] + lg2[s] - lg3[s] - lga[s] - lgb[s] + lgphi;
+        double dgN = dg3[s] - dgphi;
+        double ga = dg1[s] - dga[s] - dgN;
+        double gb = dg2[s] - dgb[s] - dgN;
+        double dD = phi * (ga - gb);
+        double dphi = fma(Dz[s], ga - gb, gb);  // D*ga + (1-D)*gb
+        ll[s] = lls;
+        if (ob.act[s]) {
+            s_ll += lls;
+            s_dD += dD;
+            s_dphi += dphi;
+            if (MODEL == 0) {
+                double dw = dD * w[s];
+                s_dDw += dw;
+                s_dDxw = fma(dw, ob.x[s], s_dDxw);
+            }
+        }
+    }
+    s_ll = group_sum<GW>(s_ll, gmask);
+    s_dD = group_sum<GW>(s_dD, gmask);
+    s_dphi = group_sum<GW>(s_dphi, gmask);
+    if (MODEL == 0) {
+        s_dDw = group_sum<GW>(s_dDw, gmask);
+        s_dDxw = group_sum<GW>(s_dDxw, gmask);
+    }
+    const bool any_bad = (__ballot_sync(gmask, bad) & gmask) != 0u;
+
+    // --- chain rule to the unconstrained parameters ----------------------------------------------
+    logp = s_ll;
+    const double gq_prior = (pr.qa - 1.0 + dj) * (1.0 - q) - (pr.qb - 1.0 + dj) * q;
+    const double gd_prior = -pr.rate * delta + dj;
+    if (MODEL == 0) {
+        grad[0] = fma(-A * q, s_dDxw, gq_prior);
+        grad[1] = fma(A * (1.0 - A), s_dDw, (pr.Aa - 1.0 + dj) * (1.0 - A) - (pr.Ab - 1.0 + dj) * A);
+        grad[2] = fma(c * (1.0 - c), s_dD, (pr.ca - 1.0 + dj) * (1.0 - c) - (pr.cb - 1.0 + dj) * c);
+        grad[3] = fma(delta, s_dphi, gd_prior);
+    } else {
+        grad[0] = fma(q * (1.0 - q), s_dD, gq_prior);
+        grad[1] = fma(delta, s_dphi, gd_prior);
+    }
+    bool fin = isfinite(logp);
+#pragma unroll
+    for (int j = 0; j < D; ++j) fin = fin && isfinite(grad[j]);
+    valid = fin && !any_bad;
+}
+
+// constrained parameters (q, A, c, phi) of an unconstrained state; null model: A = c = NaN
+template <int MODEL>
+__device__ __forceinline__ void constrain(const double (&u)[ModelDim<MODEL>::value], double phi_min, double (&th)[4]) {
+    th[0] = 1.0 / (1.0 + exp(-u[0]));
+    if (MODEL == 0) {
+        th[1] = 1.0 / (1.0 + exp(-u[1]));
+        th[2] = 1.0 / (1.0 + exp(-u[2]));
+        th[3] = exp(u[3]) + phi_min;
+    } else {
+        th[1] = nan("");
+        th[2] = nan("");
+        th[3] = exp(u[1]) + phi_min;
+    }
+}
+
+}  // namespace mdg
