@@ -69,7 +69,7 @@ enum mdg_run_kind {
 #define MDG_FIT_HAS_DIVERGENCES 0x4u /* >=1 divergent transition after warm-up (informational) */
 
 #define MDG_MAX_POSITION 64        /* max_position supported by the fit kernels */
-#define MDG_MAX_SEGMENT_ROWS 4096  /* rows of one TaxID the counts kernel can hold in one tile */
+#define MDG_MAX_SEGMENT_ROWS 2048  /* rows of one TaxID the counts kernel can hold in one tile */
 
 typedef struct mdg_ctx mdg_ctx;
 
@@ -194,7 +194,9 @@ void mdg_fit_config_default(mdg_fit_config* cfg);
  * Per-TaxID outputs (capacity n_rows entries is always enough; kept TaxIDs in input order):
  * tax id, N_alignments, first row index, dense k(z)/N(z) as [n_tax][2*max_position] with
  * slot z-1 for z>0 and max_position+|z|-1 for z<0, summed over the TaxID's rows at that z;
- * optional out_noise [n_tax][3] (normalized_noise, _forward, _reverse; pass NULL to skip).
+ * optional out_noise [n_tax][3] (normalized_noise, _forward, _reverse of fits.py:359-376, over the
+ * TaxID's rows with |z| <= max_position: CT blanked on forward rows, GA on reverse rows; pass
+ * NULL to skip).
  * Any output pointer may be NULL to skip that column.
  */
 int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows,

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
             }
             __threadfence();
             s_base = excl;
-            if (last_rows && p.n_tax_out) *p.n_tax_out = excl + running;
+            // only the LAST tile publishes the total (an earlier tile's lookahead can also reach the end of the data)
+            if (row0 + p.T >= p.n_rows && p.n_tax_out) *p.n_tax_out = excl + running;
         }
     }
     __syncthreads();

@@ -1,0 +1,159 @@
+"""Fits stage: df_counts -> (df_fit_results, df_fit_predictions), computed on the GPU(s).
+
+Keeps the reference's seams `compute_fits(df_counts, cfg, mcmc_kwargs)` and
+`get_fits(df_counts, cfg)` (fits.py:709-730, 754-807): same two DataFrames (columns, order,
+dtypes; fits.py:242-293, 632-680), same parquet cache rules, same --max-fits selection
+(fits.py:736-751). The per-TaxID Python/numpyro work (fits.py:428-469) and the
+multiprocessing fan-out (fits.py:569-626) are replaced by `mdg_fit_batch` on each GPU's
+contiguous share of the TaxID batch. The MAP fit (new) is written to fit_map/<shortname>.parquet
+so that the two reference schemas stay unchanged.
+"""
+import logging
+
+import numpy as np
+import pandas as pd
+
+from . import _lib, io, utils
+from ._abi import FIT_FAILED
+from .backend import Context
+from .counts import dense_from_df_counts
+from .parallel import run_on_gpus
+
+logger = logging.getLogger(__name__)
+
+# column order of the reference's fit_result dict (fits.py:242-293, 317-356, 374-376)
+FIT_RESULT_COLUMNS = [
+    "tax_id", "tax_name", "tax_rank", "D_max", "n_sigma", "D_max_lower_hpdi", "D_max_upper_hpdi", "q_mean",
+    "concentration_mean", "D_max_marginalized_mean", "N_alignments", "N_z1_forward", "N_z1_reverse",
+    "N_sum_forward", "N_sum_reverse", "N_sum_total", "y_sum_forward", "y_sum_reverse", "y_sum_total",
+    "n_sigma_forward", "D_max_forward", "q_mean_forward", "n_sigma_reverse", "D_max_reverse", "q_mean_reverse",
+    "asymmetry", "normalized_noise", "normalized_noise_forward", "normalized_noise_reverse",
+]
+FIT_MAP_COLUMNS = ["map_A", "map_q", "map_c", "map_phi", "map_D_max", "map_logp", "map_null_q", "map_null_phi",
+                   "map_null_logp"]
+
+_contexts = {}
+
+
+def _context(device):
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+def mcmc_kwargs_default():
+    """fits.py:792-799."""
+    return dict(progress_bar=False, num_warmup=500, num_samples=1000, num_chains=1, chain_method="sequential")
+
+
+def fit_config_from(cfg, mcmc_kwargs=None):
+    kw = dict(mcmc_kwargs_default(), **(mcmc_kwargs or {}))
+    if kw.get("num_chains", 1) != 1:
+        raise ValueError("only num_chains=1 is supported (as in the reference, fits.py:796)")
+    return _lib.default_config(num_warmup=int(kw["num_warmup"]), num_samples=int(kw["num_samples"]),
+                               seed=int(getattr(cfg, "seed", 0)))
+
+
+def extract_top_max_fits(df_counts, max_fits):
+    """fits.py:736-744: the TaxIDs with the largest sum of N_alignments over their rows."""
+    top = df_counts.groupby("tax_id", observed=True)["N_alignments"].sum().nlargest(max_fits).index
+    return df_counts[df_counts["tax_id"].isin(top)]
+
+
+def get_top_max_fits(df_counts, n_fits):
+    if n_fits is not None and n_fits > 0:
+        return extract_top_max_fits(df_counts, n_fits)
+    return df_counts
+
+
+def fit_dense(dense, cfg, fit_cfg, n_gpus=1):
+    """Run mdg_fit_batch over `n_gpus` contiguous shares of the dense batch; host-side concat."""
+    n_tax = len(dense["tax_id"])
+    n_dev = max(1, min(int(n_gpus), _lib.load().mdg_device_count() or 1))
+
+    def worker(rank, start, stop):
+        sl = slice(start, stop)
+        return _context(rank).fit_batch(dense["tax_id"][sl], dense["k"][sl], dense["N"][sl], fit_cfg,
+                                        mism12=dense["mism12"][sl] if dense.get("mism12") is not None else None)
+
+    parts = [p for p in run_on_gpus(n_tax, n_dev, worker) if p is not None]
+    return {key: np.concatenate([p[key] for p in parts]) for key in ("result", "median", "hpdi_lo", "hpdi_hi")}
+
+
+def make_df_fit_results(res, dense, cfg):
+    """fits.py:668-680: one row per fitted TaxID in df_counts order; failed fits are dropped
+    with a warning, like the reference's timed-out fits (fits.py:520-521, 603-606)."""
+    ok = (res["status"] & FIT_FAILED) == 0
+    for tax in dense["tax_id"][~ok]:
+        logger.warning("Fit: no valid fit for tax_id %s. Skipping for now", tax)
+    data = {}
+    for col in FIT_RESULT_COLUMNS:
+        if col in ("tax_name", "tax_rank", "N_alignments"):
+            data[col] = dense[col][ok]
+        elif col == "tax_id":
+            data[col] = dense["tax_id"][ok]
+        else:
+            data[col] = res[col][ok]
+    df = pd.DataFrame(data, columns=FIT_RESULT_COLUMNS)
+    df["shortname"] = cfg.shortname
+    df = utils.downcast_dataframe(df, ["tax_id", "tax_name", "tax_rank", "shortname"])
+    return df.reset_index(drop=True), ok
+
+
+def make_df_fit_predictions(out, dense, ok, cfg):
+    """fits.py:632-665: 2P rows per TaxID: tax_id, position, median, hdpi_lower, hdpi_upper (sic)."""
+    P = int(cfg.max_position)
+    z = np.arange(P) + 1
+    position = np.concatenate([z, -z])
+    n = int(ok.sum())
+    df = pd.DataFrame({
+        "tax_id": np.repeat(dense["tax_id"][ok], 2 * P),
+        "position": np.tile(position, n),
+        "median": out["median"][ok].astype(np.float64).ravel(),
+        "hdpi_lower": out["hpdi_lo"][ok].astype(np.float64).ravel(),
+        "hdpi_upper": out["hpdi_hi"][ok].astype(np.float64).ravel(),
+    })
+    df["shortname"] = cfg.shortname
+    return utils.downcast_dataframe(df, ["tax_id", "shortname"])
+
+
+def make_df_fit_map(res, dense, ok, cfg):
+    df = pd.DataFrame({"tax_id": dense["tax_id"][ok], **{c: res[c][ok] for c in FIT_MAP_COLUMNS}})
+    df["shortname"] = cfg.shortname
+    return utils.downcast_dataframe(df, ["tax_id", "shortname"])
+
+
+def compute_fits(df_counts, cfg, mcmc_kwargs=None, return_map=False):
+    """The GPU replacement of fits.compute_fits (fits.py:709-730)."""
+    dense = dense_from_df_counts(df_counts, cfg)
+    fit_cfg = fit_config_from(cfg, mcmc_kwargs)
+    out = fit_dense(dense, cfg, fit_cfg, n_gpus=getattr(cfg, "gpus", 1))
+    df_fit_results, ok = make_df_fit_results(out["result"], dense, cfg)
+    df_fit_predictions = make_df_fit_predictions(out, dense, ok, cfg)
+    if return_map:
+        return df_fit_results, df_fit_predictions, make_df_fit_map(out["result"], dense, ok, cfg)
+    return df_fit_results, df_fit_predictions
+
+
+CACHE_KEYS = ["min_alignments", "min_y_sum", "substitution_bases_forward", "substitution_bases_reverse",
+              "N_fits", "shortname", "filename", "max_position"]
+
+
+def get_fits(df_counts, cfg):
+    """fits.py:754-807: reuse both parquet files iff present, not --forced and metadata match."""
+    pq_results = io.Parquet(cfg.filename_fit_results)
+    pq_predictions = io.Parquet(cfg.filename_fit_predictions)
+    if pq_results.exists(cfg.forced) and pq_predictions.exists(cfg.forced):
+        meta = cfg.to_dict()
+        if utils.metadata_is_similar(pq_results.load_metadata(), meta, include=CACHE_KEYS) and \
+                utils.metadata_is_similar(pq_predictions.load_metadata(), meta, include=CACHE_KEYS):
+            logger.info("Fit: Loading fits from parquet-file.")
+            return pq_results.load(), pq_predictions.load()
+    logger.info("Fit: Generating fits and saving to file.")
+    df_top = get_top_max_fits(df_counts, cfg.N_fits)
+    df_fit_results, df_fit_predictions, df_fit_map = compute_fits(df_top, cfg, mcmc_kwargs_default(), return_map=True)
+    meta = cfg.to_dict()
+    pq_results.save(df_fit_results, metadata=meta)
+    pq_predictions.save(df_fit_predictions, metadata=meta)
+    io.Parquet(cfg.filename_fit_map).save(df_fit_map, metadata=meta)
+    return df_fit_results, df_fit_predictions

@@ -1,0 +1,129 @@
+"""The oracle's NUTS (restating numpyro 0.4.1) pinned against an independent sampler: a long
+random-walk Metropolis chain on the same unconstrained log density. Also: determinism and the
+partition-independence property (results depend on (seed, tax_id) only)."""
+import numpy as np
+
+from conftest import mcse_batch_means
+
+
+def synthetic_taxon(seed, n_lo=200, n_hi=3000, A=0.25, q=0.35, c=0.02, phi=300.0):
+    rng = np.random.default_rng(seed)
+    N = rng.integers(n_lo, n_hi, 30).astype(np.uint32)
+    z = np.r_[np.arange(15), np.arange(15)]
+    Dz = A * (1 - q) ** z + c
+    p = rng.beta(Dz * phi, (1 - Dz) * phi)
+    k = rng.binomial(N, p).astype(np.uint32)
+    return k, N
+
+
+def rwm_chain(oracle, k, N, model, n_steps, seed):
+    """Adaptive-then-frozen random-walk Metropolis on u with the oracle's log density (+Jacobian)."""
+    rng = np.random.default_rng(seed)
+    D = 4 if model == 0 else 2
+
+    def logp(u):
+        uu = np.zeros(4)
+        uu[:D] = u
+        v = oracle.logp_grad(k, N, uu[None, :], model=model, with_jacobian=True)[0][0]
+        return v if np.isfinite(v) else -np.inf
+
+    m = oracle.map_fit(k, N, model=model)
+    lg = lambda p: np.log(p / (1 - p))  # noqa: E731
+    u = np.array([lg(m["q"]), lg(m["A"]), lg(m["c"]), np.log(m["phi"] - 2)]) if model == 0 else \
+        np.array([lg(m["q"]), np.log(m["phi"] - 2)])
+    lp = logp(u)
+    scale = np.full(D, 0.1)
+    pilot = []
+    for i in range(6000):  # pilot: per-coordinate scales
+        prop = u + scale * rng.normal(size=D)
+        lpp = logp(prop)
+        if np.log(rng.random()) < lpp - lp:
+            u, lp = prop, lpp
+        pilot.append(u.copy())
+    cov = np.cov(np.array(pilot[2000:]).T) * (2.4 ** 2 / D)
+    L = np.linalg.cholesky(cov + 1e-10 * np.eye(D))
+    out = np.empty((n_steps, D))
+    for i in range(n_steps):
+        prop = u + L @ rng.normal(size=D)
+        lpp = logp(prop)
+        if np.log(rng.random()) < lpp - lp:
+            u, lp = prop, lpp
+        out[i] = u
+    return out
+
+
+def test_nuts_posterior_matches_independent_rwm(oracle):
+    k, N = synthetic_taxon(11)
+    cfg = oracle.default_config(num_warmup=500, num_samples=4000)
+    sg = lambda x: 1 / (1 + np.exp(-x))  # noqa: E731
+    # PMD
+    nuts = oracle.nuts_run(k, N, tax_id=4242, run_kind=0, cfg=cfg)
+    assert nuts["rc"] == 0
+    s = nuts["samples"]
+    rwm = rwm_chain(oracle, k, N, 0, 60000, seed=5)
+    pairs = {
+        "q": (s[:, 0], sg(rwm[:, 0])),
+        "D_max": (s[:, 1] + s[:, 2], sg(rwm[:, 1]) + sg(rwm[:, 2])),
+        "log_delta": (np.log(s[:, 3] - 2), rwm[:, 3]),
+    }
+    for name, (a, b) in pairs.items():
+        se = np.hypot(mcse_batch_means(a), mcse_batch_means(b, 30))
+        assert abs(a.mean() - b.mean()) < 4 * se, (name, a.mean(), b.mean(), se)
+        assert 0.8 < a.std() / b.std() < 1.25, (name, a.std(), b.std())
+    # null
+    nuts = oracle.nuts_run(k, N, tax_id=4242, run_kind=1, cfg=cfg)
+    s = nuts["samples"]
+    rwm = rwm_chain(oracle, k, N, 1, 40000, seed=6)
+    a, b = s[:, 0], sg(rwm[:, 0])
+    se = np.hypot(mcse_batch_means(a), mcse_batch_means(b, 30))
+    assert abs(a.mean() - b.mean()) < 4 * se
+    assert 0.8 < a.std() / b.std() < 1.25
+
+
+def test_nuts_sampler_diagnostics(oracle):
+    k, N = synthetic_taxon(12)
+    out = oracle.nuts_run(k, N, tax_id=7, run_kind=0)
+    assert 0.6 < out["mean_accept"] <= 1.0          # target_accept_prob = 0.8
+    assert 1e-3 < out["step_size"] < 5.0
+    assert 1500 * 1 <= out["n_grad"] <= 1500 * 1023  # max_tree_depth = 10
+
+
+def test_fit_is_deterministic_and_partition_independent(oracle):
+    taxa = [synthetic_taxon(20 + i) for i in range(3)]
+    tid = np.array([101, 202, 303], np.int64)
+    k = np.stack([t[0] for t in taxa])
+    N = np.stack([t[1] for t in taxa])
+    cfg = oracle.default_config(num_warmup=60, num_samples=80)
+    full = oracle.fit_batch(tid, k, N, cfg)["result"]
+    again = oracle.fit_batch(tid, k, N, cfg)["result"]
+    assert full.tobytes() == again.tobytes()
+    part = oracle.fit_batch(tid[1:2], k[1:2], N[1:2], cfg)["result"]
+    assert part[0].tobytes() == full[1].tobytes()
+    perm = oracle.fit_batch(tid[::-1].copy(), k[::-1].copy(), N[::-1].copy(), cfg)["result"]
+    assert perm[0].tobytes() == full[2].tobytes()
+    other_seed = oracle.fit_batch(tid, k, N, oracle.default_config(num_warmup=60, num_samples=80, seed=1))["result"]
+    assert other_seed["q_mean"][0] != full["q_mean"][0]
+
+
+def test_fit_result_fields_are_consistent(oracle):
+    k, N = synthetic_taxon(31)
+    cfg = oracle.default_config(num_warmup=200, num_samples=400)
+    out = oracle.fit_batch(np.array([5], np.int64), k[None], N[None], cfg, want_samples=True, want_waic=True)
+    r = out["result"][0]
+    assert r["status"] & 1 == 0
+    assert r["N_z1_forward"] == N[0] and r["N_z1_reverse"] == N[15]
+    assert r["N_sum_total"] == N.sum() and r["y_sum_forward"] == k[:15].sum()
+    s = out["samples"][0, 0]
+    assert abs(r["q_mean"] - s[:, 0].mean()) < 1e-12
+    assert abs(r["D_max_marginalized_mean"] - (s[:, 1] + s[:, 2]).mean()) < 1e-12
+    assert abs(r["concentration_mean"] - s[:, 3].mean()) < 1e-9
+    # n_sigma recomputed from the per-position WAIC blocks (fits.py:194-201)
+    w = out["waic"][0]
+    wi = lambda run: -2 * (w[run, 0] - w[run, 1])  # noqa: E731
+    d = wi(0) - wi(1)
+    assert abs(r["n_sigma"] - (wi(1).sum() - wi(0).sum()) / np.sqrt(30 * d.var())) < 1e-9
+    # the damage signal injected (A = 0.25) must be significant
+    assert r["n_sigma"] > 3 and 0.15 < r["D_max"] < 0.4
+    assert r["D_max_lower_hpdi"] <= r["D_max"] <= r["D_max_upper_hpdi"]
+    # predictive median at z = 1 is a multiple of 1/N(z=1) or a half step
+    assert abs(r["D_max"] * N[0] * 2 - round(r["D_max"] * N[0] * 2)) < 1e-6
