@@ -386,8 +386,11 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
                  aligned16(cl.counts16) && (cl.stride % 4 == 0);
 
     // ---- tiling ladder: widen the lookahead if a TaxID does not fit ----
-    static const int ladder_T[3] = {1024, 1024, 512};
-    static const int ladder_L[3] = {128, 512, MDG_MAX_SEGMENT_ROWS};
+    // output bases 16-byte aligned -> 128-bit stores
+    cl.vec_out = aligned16(cl.n_fwd_row) && aligned16(cl.n_rev_row) && aligned16(cl.f_fwd_row) && aligned16(cl.f_rev_row) &&
+                 aligned16(cl.z_row) && aligned16(cl.y_row) && aligned16(cl.keep_row);
+    static const int ladder_T[3] = {448, 512, 512};
+    static const int ladder_L[3] = {64, 512, MDG_MAX_SEGMENT_ROWS};
     int rc = ctx->buf[2].ensure(64);
     if (rc) return rc;
     long long* d_ntax = ctx->buf[2].as<long long>();
@@ -395,13 +398,20 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
     unsigned int* d_ticket = reinterpret_cast<unsigned int*>(d_ntax + 2);
     int h_err = 0;
     long long h_ntax = 0;
+    const size_t row_bytes = (size_t)kCountsBytesPerRow + 4 * (size_t)cl.ncols;
+    const size_t fixed_bytes = 16 + 16 + (size_t)kCountsWarps * 2 * R * 4 + 256;
     for (int step = 0; step < 3; ++step) {
         cl.T = ladder_T[step];
         cl.L = ladder_L[step];
+        // shrink the tile (never the lookahead) until it fits the 227 KB of shared memory
+        while (cl.T > 16 && fixed_bytes + row_bytes * (size_t)(cl.T + cl.L) > 227 * 1024 - 1024) cl.T -= 16;
         const int cap = cl.T + cl.L;
-        const size_t smem = (size_t)8 * (cap + 2) + (size_t)4 * cl.ncols * cap + (size_t)4 * cap + (size_t)4 * (cap + 4) +
-                            (size_t)3 * cap + (size_t)kCountsWarps * 2 * R * 4 + 64;
-        if (smem > 227 * 1024) { set_error("mdg_counts_reduce: tile does not fit shared memory"); return MDG_ERR_SEGMENT_TOO_LONG; }
+        const size_t smem = fixed_bytes + row_bytes * (size_t)cap;
+        if (smem > 227 * 1024 - 1024) {
+            set_error("mdg_counts_reduce: a TaxID spans more rows than one shared-memory tile can stage (%d with these options)",
+                      (int)((227 * 1024 - 1024 - fixed_bytes) / row_bytes) - 16);
+            return MDG_ERR_SEGMENT_TOO_LONG;
+        }
         const long long n_tiles = (n_rows + cl.T - 1) / cl.T;
         rc = ctx->buf[3].ensure((size_t)n_tiles * 8);
         if (rc) return rc;

@@ -4,20 +4,28 @@
 // handling 117-129, fillna 175-176, y_sum_total 179-204, cuts 207-209) and the dense extraction
 // of fits.py:398-419; optionally the noise statistic of fits.py:359-376.
 //
-// HBM-bound (111 algorithmic bytes per row). Design: one CTA per tile of T rows
-// plus an L-row lookahead; the tile's SoA column chunks are brought into shared memory with 1-D
-// TMA bulk copies (cp.async.bulk -> UBLKCP) signalled on one mbarrier; the CTA owns every TaxID
-// whose first row lies in [row0, row0+T), so no carry crosses tiles and the only inter-CTA
-// traffic is a decoupled look-back on the count of kept TaxIDs (stable compaction of the dense
-// output). Inside the tile one warp handles one TaxID at a time (lane = row, i.e. position),
-// reducing with shuffles — the same lane<->position mapping as the fit kernels.
+// HBM-bound (111 algorithmic bytes per row). Design:
+//   * one CTA per tile of T rows plus an L-row lookahead; the tile's SoA column chunks come into
+//     shared memory through 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) on one mbarrier;
+//   * the CTA owns every TaxID whose first row lies in [row0, row0+T): no carry crosses tiles,
+//     the only inter-CTA traffic is a warp-wide decoupled look-back on the count of kept TaxIDs
+//     (stable compaction of the dense output);
+//   * per-row work is vectorised: one thread handles 4 consecutive rows with 128-bit shared
+//     loads, results are staged in shared memory and leave with 128-bit coalesced global stores
+//     (tile starts are 16-byte aligned for every column type);
+//   * per-TaxID sums are a short serial loop of one thread per TaxID over staged values; the
+//     dense k/N (and the optional noise) of KEPT TaxIDs use one warp per TaxID, lane = row.
+// The first version (one warp per TaxID for everything) was instruction-issue bound at 30 warp
+// instructions per row (profiles/r01_counts_ncu.md); this layout needs a few.
 #pragma once
 #include "mdg_common.cuh"
 
 namespace mdg {
 
-constexpr int kCountsThreads = 256;
+constexpr int kCountsThreads = 128;
 constexpr int kCountsWarps = kCountsThreads / 32;
+// shared bytes per staged row, without the count columns (4 bytes per staged column on top)
+constexpr int kCountsBytesPerRow = 8 + 4 + 1 + 1 + 16 + 4 + 1 + 1 + 4 + 8 + 1;
 
 enum CountsError : int { CE_NONE = 0, CE_SEGMENT_TOO_LONG = 1, CE_OVERFLOW = 2 };
 
@@ -49,11 +57,12 @@ struct CountsLaunch {
     uint32_t* out_N;
     double* out_noise;
     // tiling
-    int T, L;               // owned rows per tile, lookahead rows
+    int T, L;               // owned rows per tile (multiple of 16), lookahead rows; T + L multiple of 16
     int ncols;              // count columns staged in shared memory
     int col_id[16];         // which of the 16 columns
     int col_slot[16];       // column -> staged slot (or -1)
     int use_tma;            // all column bases 16-byte aligned
+    int vec_out;            // per-row output bases 16-byte aligned -> 128-bit stores
     unsigned int* tile_ticket;
     unsigned long long* tile_state;  // decoupled look-back: flag << 62 | value
     long long* n_tax_out;            // device scalar
@@ -67,43 +76,47 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
-    return __shfl_xor_sync(0xffffffffu, v, o);
-}
-
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_u64(v, o);
-    return v;
-}
-
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
+// float32(double(k) / double(n)) with 0/0 -> 0 (counts.py:99, 254). Operands are forced into
+// the normal range so that the FP64 division never leaves its fast path.
+__device__ __forceinline__ float error_rate(uint32_t k, uint32_t n) {
+    const double q = (double)(k ? k : 1u) / (double)(n ? n : 1u);
+    return (k && n) ? (float)q : 0.0f;
+}
+
 __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const CountsLaunch p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cap = p.T + p.L;  // rows staged per tile (multiple of 16)
-    // shared layout: [tax: (cap+2) i64][counts: ncols*cap u32][nal: cap u32][seg_start: cap+4 i32]
-    //                [rev: cap u8][pos: cap u8][seg_kept: cap u8][dense: warps*2*2P u32] [misc]
-    long long* s_tax = reinterpret_cast<long long*>(smem_raw);       // s_tax[1+i] = tax of staged row i; s_tax[0] = row before
+    // ---- shared layout (every array starts 16-byte aligned because cap % 16 == 0) ----
+    long long* s_tax = reinterpret_cast<long long*>(smem_raw);  // s_tax[2+i] = tax id of staged row i; s_tax[1] = row before
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_tax + cap + 2);
     uint32_t* s_nal = s_cnt + (size_t)p.ncols * cap;
-    int* s_seg = reinterpret_cast<int*>(s_nal + cap);
-    uint8_t* s_rev = reinterpret_cast<uint8_t*>(s_seg + cap + 4);  // cap % 16 == 0 keeps 16-byte alignment
+    uint32_t* o_nf = s_nal + cap;
+    uint32_t* o_nr = o_nf + cap;
+    float* o_ff = reinterpret_cast<float*>(o_nr + cap);
+    float* o_fr = o_ff + cap;
+    uint32_t* o_yc = reinterpret_cast<uint32_t*>(o_fr + cap);   // y contribution of the row; later: rank of the segment
+    int* s_seg = reinterpret_cast<int*>(o_yc + cap);            // head row of segment s; s_seg[nseg] = nload
+    unsigned long long* s_ysum = reinterpret_cast<unsigned long long*>(s_seg + cap + 4);
+    uint8_t* s_rev = reinterpret_cast<uint8_t*>(s_ysum + cap);
     uint8_t* s_pos = s_rev + cap;
-    uint8_t* s_kept = s_pos + cap;
-    uint32_t* s_dense = reinterpret_cast<uint32_t*>(s_kept + cap);   // cap is a multiple of 16 -> aligned
+    int8_t* o_z = reinterpret_cast<int8_t*>(s_pos + cap);
+    uint8_t* o_head = reinterpret_cast<uint8_t*>(o_z + cap);
+    uint8_t* s_kept = o_head + cap;
+    uint32_t* s_dense = reinterpret_cast<uint32_t*>(s_kept + cap);  // [warps][2][2P]
     __shared__ uint64_t s_bar;
     __shared__ unsigned int s_tile;
     __shared__ int s_warp_cnt[kCountsWarps];
-    __shared__ int s_nseg, s_nowned;
+    __shared__ int s_nseg, s_nowned, s_kept_total;
     __shared__ long long s_base;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) s_tile = atomicAdd(p.tile_ticket, 1u);
+    if (tid == 0) { s_tile = atomicAdd(p.tile_ticket, 1u); s_nowned = 0; }
     __syncthreads();
     const unsigned tile = s_tile;
     const long long row0 = (long long)tile * p.T;
@@ -111,6 +124,7 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
     const int nload = (int)(remaining < cap ? remaining : cap);
     const int nown = nload < p.T ? nload : p.T;
     const bool last_rows = (row0 + nload == p.n_rows);
+    const int P = p.P, R = 2 * P;
 
     // ---------------- stage the tile ----------------
     const bool tma = p.use_tma && (nload % 16 == 0);
@@ -121,19 +135,20 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
             const uint32_t total = (uint32_t)nload * (8u + 4u + 1u + 1u + 4u * (uint32_t)p.ncols);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s_bar)), "r"(total) : "memory");
             tma_load_1d(s_tax + 2, p.tax_id + row0, (uint32_t)nload * 8u, &s_bar);
+            for (int c = 0; c < p.ncols; ++c)
+                tma_load_1d(s_cnt + (size_t)c * cap, p.counts16 + (long long)p.col_id[c] * p.stride + row0, (uint32_t)nload * 4u, &s_bar);
             tma_load_1d(s_nal, p.n_align + row0, (uint32_t)nload * 4u, &s_bar);
             tma_load_1d(s_rev, p.is_rev + row0, (uint32_t)nload, &s_bar);
             tma_load_1d(s_pos, p.pos0 + row0, (uint32_t)nload, &s_bar);
-            for (int c = 0; c < p.ncols; ++c)
-                tma_load_1d(s_cnt + (size_t)c * cap, p.counts16 + (long long)p.col_id[c] * p.stride + row0, (uint32_t)nload * 4u, &s_bar);
             s_tax[1] = row0 > 0 ? p.tax_id[row0 - 1] : 0;
+            // one thread sleeps on the barrier; the rest of the CTA waits in bar.sync (no issue slots)
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&s_bar)), "r"(0), "r"(2000000) : "memory");
+            }
         }
         __syncthreads();
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(smem_u32(&s_bar)), "r"(0) : "memory");
-        }
     } else {
         for (int i = tid; i < nload; i += kCountsThreads) {
             s_tax[2 + i] = p.tax_id[row0 + i];
@@ -150,95 +165,120 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
     }
     const long long* taxv = s_tax + 2;  // taxv[i], i in [-1, nload)
 
-    // ---------------- segment heads: ordered compaction of head indices ----------------
-    // each warp scans a contiguous range of rows; two passes (count, then write)
-    const int per_warp = ((nload + kCountsWarps - 1) / kCountsWarps + 31) & ~31;
-    const int w_lo = warp * per_warp, w_hi = min(nload, w_lo + per_warp);
-    int cnt = 0;
-    for (int b = w_lo; b < w_hi; b += 32) {
-        const int i = b + lane;
-        const bool head = (i < w_hi) && ((row0 + i == 0) || (taxv[i] != taxv[i - 1]));
-        cnt += __popc(__ballot_sync(0xffffffffu, head));
-    }
-    if (lane == 0) s_warp_cnt[warp] = cnt;
-    __syncthreads();
-    int off = 0;
-    for (int w = 0; w < warp; ++w) off += s_warp_cnt[w];
-    for (int b = w_lo; b < w_hi; b += 32) {
-        const int i = b + lane;
-        const bool head = (i < w_hi) && ((row0 + i == 0) || (taxv[i] != taxv[i - 1]));
-        const unsigned m = __ballot_sync(0xffffffffu, head);
-        if (head) s_seg[off + __popc(m & ((1u << lane) - 1u))] = i;
-        off += __popc(m);
-    }
-    if (tid == 0) {
-        int n = 0;
-        for (int w = 0; w < kCountsWarps; ++w) n += s_warp_cnt[w];
-        s_nseg = n;
-        s_seg[n] = nload;  // terminator
-    }
-    __syncthreads();
-    const int nseg = s_nseg;
-    // owned segments: heads in [0, nown). heads are sorted, so count them with a strided scan
-    if (tid == 0) s_nowned = 0;
-    __syncthreads();
-    {
-        int local = 0;
-        for (int s = tid; s < nseg; s += kCountsThreads) local += (s_seg[s] < nown);
-        local = __reduce_add_sync(0xffffffffu, local);
-        if (lane == 0 && local) atomicAdd(&s_nowned, local);
-    }
-    __syncthreads();
-    const int nowned = s_nowned;
-    // the last owned segment must terminate inside the staged rows (or at the end of the data)
-    if (tid == 0 && nowned > 0) {
-        const bool terminated = (nowned < nseg) || last_rows;
-        if (!terminated) atomicMax(p.error_flag, (int)CE_SEGMENT_TOO_LONG);
-    }
-
-    const int P = p.P, R = 2 * P;
     const int sf0 = p.col_slot[p.fwd_ref * 4], sr0 = p.col_slot[p.rev_ref * 4];
     const int skf = p.col_slot[p.fwd_ref * 4 + p.fwd_obs], skr = p.col_slot[p.rev_ref * 4 + p.rev_obs];
 
-    // ---------------- pass 1: per-row values, y_sum_total, cut flags ----------------
-    for (int s = warp; s < nowned; s += kCountsWarps) {
-        const int a = s_seg[s], b = s_seg[s + 1];
-        unsigned long long ysum = 0;
-        for (int r = a + lane; r < b; r += 32) {
-            unsigned long long nf = 0, nr = 0;
+    // ---------------- phase 1: 4 rows per thread; per-row values + ordered list of TaxID heads ----------------
+    const int ngroups = (nload + 3) >> 2;
+    int seg_base = 0;  // heads found in earlier trips of this loop
+    for (int g0 = 0; g0 < ngroups; g0 += kCountsThreads) {
+        const int g = g0 + tid;
+        const int i0 = g << 2;
+        int nheads = 0;
+        uint32_t headbits = 0;
+        if (g < ngroups) {
+            uint32_t nf[4] = {0, 0, 0, 0}, nr[4] = {0, 0, 0, 0};
+            uint32_t ovfmask = 0;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-                nf += s_cnt[(size_t)(sf0 + o) * cap + r];
-                nr += s_cnt[(size_t)(sr0 + o) * cap + r];
+                const uint4 a = *reinterpret_cast<const uint4*>(s_cnt + (size_t)(sf0 + o) * cap + i0);
+                const uint4 b = *reinterpret_cast<const uint4*>(s_cnt + (size_t)(sr0 + o) * cap + i0);
+                const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t sa = nf[j] + av[j], sb = nr[j] + bv[j];
+                    ovfmask |= (uint32_t)((sa < nf[j]) | (sb < nr[j])) << j;
+                    nf[j] = sa; nr[j] = sb;
+                }
             }
-            const uint32_t kf = s_cnt[(size_t)skf * cap + r], kr = s_cnt[(size_t)skr * cap + r];
-            const int zabs = (int)s_pos[r] + 1;
-            const bool rev = s_rev[r] != 0;
-            if (nf > 0xFFFFFFFFull || nr > 0xFFFFFFFFull) atomicMax(p.error_flag, (int)CE_OVERFLOW);
-            const long long g = row0 + r;
-            if (p.n_fwd_row) p.n_fwd_row[g] = (uint32_t)nf;
-            if (p.n_rev_row) p.n_rev_row[g] = (uint32_t)nr;
-            if (p.f_fwd_row) p.f_fwd_row[g] = nf ? (float)((double)kf / (double)nf) : 0.0f;
-            if (p.f_rev_row) p.f_rev_row[g] = nr ? (float)((double)kr / (double)nr) : 0.0f;
-            if (p.z_row) p.z_row[g] = (int8_t)(rev ? -zabs : zabs);
-            if (zabs <= P) ysum += rev ? kr : kf;
+            const uint4 kfv = *reinterpret_cast<const uint4*>(s_cnt + (size_t)skf * cap + i0);
+            const uint4 krv = *reinterpret_cast<const uint4*>(s_cnt + (size_t)skr * cap + i0);
+            const uint32_t kf[4] = {kfv.x, kfv.y, kfv.z, kfv.w}, kr[4] = {krv.x, krv.y, krv.z, krv.w};
+            const uchar4 pv = *reinterpret_cast<const uchar4*>(s_pos + i0);
+            const uchar4 rv = *reinterpret_cast<const uchar4*>(s_rev + i0);
+            const int pos[4] = {pv.x, pv.y, pv.z, pv.w};
+            const bool rev[4] = {rv.x != 0, rv.y != 0, rv.z != 0, rv.w != 0};
+            long long tx[5];
+            tx[0] = taxv[i0 - 1];
+            {
+                const longlong2 t01 = *reinterpret_cast<const longlong2*>(taxv + i0);
+                const longlong2 t23 = *reinterpret_cast<const longlong2*>(taxv + i0 + 2);
+                tx[1] = t01.x; tx[2] = t01.y; tx[3] = t23.x; tx[4] = t23.y;
+            }
+            float ff[4], fr[4];
+            uint32_t yc[4], zpack = 0;
+            bool ovf = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j;
+                const bool valid = i < nload;
+                ovf |= valid && ((ovfmask >> j) & 1u);
+                const int zabs = pos[j] + 1;
+                ff[j] = error_rate(kf[j], nf[j]);
+                fr[j] = error_rate(kr[j], nr[j]);
+                yc[j] = (valid && zabs <= P) ? (rev[j] ? kr[j] : kf[j]) : 0u;
+                const int z = rev[j] ? -zabs : zabs;
+                zpack |= ((uint32_t)(uint8_t)(int8_t)z) << (8 * j);
+                const bool head = valid && ((row0 + i == 0) || (tx[j + 1] != tx[j]));
+                headbits |= (head ? 1u : 0u) << (8 * j);
+                nheads += head ? 1 : 0;
+            }
+            if (ovf) atomicMax(p.error_flag, (int)CE_OVERFLOW);
+            *reinterpret_cast<uint4*>(o_nf + i0) = make_uint4(nf[0], nf[1], nf[2], nf[3]);
+            *reinterpret_cast<uint4*>(o_nr + i0) = make_uint4(nr[0], nr[1], nr[2], nr[3]);
+            *reinterpret_cast<float4*>(o_ff + i0) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+            *reinterpret_cast<float4*>(o_fr + i0) = make_float4(fr[0], fr[1], fr[2], fr[3]);
+            *reinterpret_cast<uint4*>(o_yc + i0) = make_uint4(yc[0], yc[1], yc[2], yc[3]);
+            *reinterpret_cast<uint32_t*>(o_z + i0) = zpack;
+            *reinterpret_cast<uint32_t*>(o_head + i0) = headbits;
         }
-        ysum = warp_sum_u64(ysum);
-        bool any_keep = false;
-        for (int r = a + lane; r < b; r += 32) {
-            const int zabs = (int)s_pos[r] + 1;
-            const bool keep = (s_nal[r] >= p.min_align) && (ysum >= p.min_y) && (zabs <= P);
-            const long long g = row0 + r;
-            if (p.y_row) p.y_row[g] = ysum;
-            if (p.keep_row) p.keep_row[g] = keep ? 1 : 0;
-            any_keep |= keep;
+        // ordered compaction of the head rows: warp scan + block offsets
+        int incl = nheads;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp_cnt[warp] = incl;
+        __syncthreads();
+        int off = seg_base + incl - nheads, total = 0;
+#pragma unroll
+        for (int w = 0; w < kCountsWarps; ++w) { const int c = s_warp_cnt[w]; off += (w < warp) ? c : 0; total += c; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((headbits >> (8 * j)) & 1u) s_seg[off++] = i0 + j;
+        seg_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) { s_nseg = seg_base; s_seg[seg_base] = nload; }
+    __syncthreads();
+    const int nseg = s_nseg;
+
+    // ---------------- phase 2: one thread per owned TaxID: y_sum_total and the cut ----------------
+    {
+        int local_owned = 0;
+        for (int s = tid; s < nseg; s += kCountsThreads) {
+            const int a = s_seg[s];
+            if (a >= nown) break;  // heads are sorted: the rest belongs to the next tile
+            ++local_owned;
+            const int b = s_seg[s + 1];
+            unsigned long long ysum = 0;
+            bool any_row = false;
+            for (int r = a; r < b; ++r) {
+                ysum += o_yc[r];
+                const int z = o_z[r];
+                any_row |= (s_nal[r] >= p.min_align) && ((z < 0 ? -z : z) <= P);
+            }
+            s_ysum[s] = ysum;
+            s_kept[s] = (any_row && ysum >= p.min_y) ? 1 : 0;
         }
-        any_keep = __any_sync(0xffffffffu, any_keep);
-        if (lane == 0) s_kept[s] = any_keep ? 1 : 0;
+        local_owned = __reduce_add_sync(0xffffffffu, local_owned);
+        if (lane == 0 && local_owned) atomicAdd(&s_nowned, local_owned);
     }
     __syncthreads();
+    const int nowned = s_nowned;
+    // the last owned TaxID must end inside the staged rows (or at the end of the data)
+    if (tid == 0 && nowned > 0 && !((nowned < nseg) || last_rows)) atomicMax(p.error_flag, (int)CE_SEGMENT_TOO_LONG);
 
-    // ---------------- stable compaction index: block scan + decoupled look-back ----------------
+    // ---------------- phase 3 (warp 0): ranks of the kept TaxIDs, publish the tile aggregate ----------------
+    uint32_t* s_rank = o_yc;  // o_yc is dead after phase 2
     if (warp == 0) {
         int running = 0;
         for (int b0 = 0; b0 < nowned; b0 += 32) {
@@ -246,29 +286,100 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
             const int v = (s < nowned) ? (int)s_kept[s] : 0;
             int incl = v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (s < nowned) s_rank[s] = (uint32_t)(running + incl - v);
             running += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (lane == 0) {
-            // publish aggregate, look back, publish inclusive prefix
-            const unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
-            volatile unsigned long long* st = p.tile_state;
-            long long excl = 0;
-            if (tile == 0) {
-                st[0] = FLAG_INC | (unsigned long long)running;
-            } else {
-                st[tile] = FLAG_AGG | (unsigned long long)running;
+            s_kept_total = running;
+            if (tile > 0) {
+                volatile unsigned long long* st = p.tile_state;
+                st[tile] = (1ull << 62) | (unsigned long long)running;
                 __threadfence();
-                long long t = (long long)tile - 1;
-                while (t >= 0) {
-                    unsigned long long v;
-                    do { v = st[t]; } while ((v >> 62) == 0ull);
-                    excl += (long long)(v & VMASK);
-                    if ((v >> 62) == 2ull) break;
-                    --t;
-                }
-                st[tile] = FLAG_INC | (unsigned long long)(excl + running);
             }
+        }
+        __syncwarp();
+    }
+
+    // ---------------- phase 4: per-row outputs of the owned rows, 128-bit coalesced ----------------
+    if (nowned > 0) {
+        const int a0 = s_seg[0], a1 = s_seg[nowned];
+        for (int g = tid + (a0 >> 2); g < ((a1 + 3) >> 2); g += kCountsThreads) {
+            const int i0 = g << 2;
+            // TaxID of the first owned row of this group: binary search in the sorted head list
+            const int ifirst = i0 < a0 ? a0 : i0;
+            int lo = 0, hi = nowned - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_seg[mid] <= ifirst) lo = mid; else hi = mid - 1; }
+            int s = lo;
+            const uint32_t headbits = *reinterpret_cast<const uint32_t*>(o_head + i0);
+            const uint32_t zpack = *reinterpret_cast<const uint32_t*>(o_z + i0);
+            const uint4 nal4 = *reinterpret_cast<const uint4*>(s_nal + i0);
+            const uint32_t nal[4] = {nal4.x, nal4.y, nal4.z, nal4.w};
+            unsigned long long y[4];
+            uint32_t keeppack = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j;
+                if (i > ifirst && ((headbits >> (8 * j)) & 1u)) ++s;
+                const int z = (int)(int8_t)((zpack >> (8 * j)) & 0xffu);
+                const unsigned long long ys = s_ysum[s < nowned ? s : nowned - 1];
+                y[j] = ys;
+                const bool keep = (nal[j] >= p.min_align) && (ys >= p.min_y) && ((z < 0 ? -z : z) <= P);
+                keeppack |= (keep ? 1u : 0u) << (8 * j);
+            }
+            const long long gi = row0 + i0;
+            if (p.vec_out && i0 >= a0 && i0 + 4 <= a1) {
+                if (p.n_fwd_row) *reinterpret_cast<uint4*>(p.n_fwd_row + gi) = *reinterpret_cast<const uint4*>(o_nf + i0);
+                if (p.n_rev_row) *reinterpret_cast<uint4*>(p.n_rev_row + gi) = *reinterpret_cast<const uint4*>(o_nr + i0);
+                if (p.f_fwd_row) *reinterpret_cast<float4*>(p.f_fwd_row + gi) = *reinterpret_cast<const float4*>(o_ff + i0);
+                if (p.f_rev_row) *reinterpret_cast<float4*>(p.f_rev_row + gi) = *reinterpret_cast<const float4*>(o_fr + i0);
+                if (p.y_row) {
+                    *reinterpret_cast<ulonglong2*>(p.y_row + gi) = make_ulonglong2(y[0], y[1]);
+                    *reinterpret_cast<ulonglong2*>(p.y_row + gi + 2) = make_ulonglong2(y[2], y[3]);
+                }
+                if (p.z_row) *reinterpret_cast<uint32_t*>(p.z_row + gi) = zpack;
+                if (p.keep_row) *reinterpret_cast<uint32_t*>(p.keep_row + gi) = keeppack;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j;
+                    if (i < a0 || i >= a1) continue;
+                    if (p.n_fwd_row) p.n_fwd_row[gi + j] = o_nf[i];
+                    if (p.n_rev_row) p.n_rev_row[gi + j] = o_nr[i];
+                    if (p.f_fwd_row) p.f_fwd_row[gi + j] = o_ff[i];
+                    if (p.f_rev_row) p.f_rev_row[gi + j] = o_fr[i];
+                    if (p.y_row) p.y_row[gi + j] = y[j];
+                    if (p.z_row) p.z_row[gi + j] = (int8_t)((zpack >> (8 * j)) & 0xffu);
+                    if (p.keep_row) p.keep_row[gi + j] = (uint8_t)((keeppack >> (8 * j)) & 1u);
+                }
+            }
+        }
+    }
+
+    // ---------------- phase 5 (warp 0): decoupled look-back, 32 predecessor tiles at a time ----------------
+    if (warp == 0) {
+        const unsigned long long VMASK = (1ull << 62) - 1;
+        volatile unsigned long long* st = p.tile_state;
+        const int running = s_kept_total;
+        long long excl = 0;
+        if (tile > 0) {
+            long long hi = (long long)tile - 1;
+            for (;;) {
+                const long long t = hi - lane;
+                unsigned long long v = 2ull << 62;  // tiles before 0 act as an inclusive prefix of 0
+                if (t >= 0) { do { v = st[t]; } while ((v >> 62) == 0ull); }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+                const int stop = inc_mask ? __ffs(inc_mask) - 1 : 31;  // nearest inclusive prefix
+                long long contrib = (lane <= stop) ? (long long)(v & VMASK) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                excl += contrib;
+                if (inc_mask) break;
+                hi -= 32;
+            }
+        }
+        if (lane == 0) {
+            st[tile] = (2ull << 62) | (unsigned long long)(excl + running);
             __threadfence();
             s_base = excl;
             // only the LAST tile publishes the total (an earlier tile's lookahead can also reach the end of the data)
@@ -277,22 +388,14 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
     }
     __syncthreads();
     const long long base = s_base;
+    if (s_kept_total == 0) return;
 
-    // ---------------- pass 2: dense k/N (+ noise) of the kept TaxIDs ----------------
+    // ---------------- phase 6: dense k/N (+ noise) of the kept TaxIDs, one warp per TaxID ----------------
     uint32_t* dk = s_dense + (size_t)warp * 2 * R;
     uint32_t* dN = dk + R;
-    // rank of segment s among kept = number of kept segments before it (recomputed per warp chunk)
-    int rank_before = 0;  // kept count in segments [0, chunk start)
-    for (int b0 = 0; b0 < nowned; b0 += kCountsWarps) {
-        const int s = b0 + warp;
-        // count kept among [b0, s) cheaply: kCountsWarps is 8
-        int my_rank = rank_before;
-        for (int q = b0; q < s && q < nowned; ++q) my_rank += s_kept[q];
-        int chunk_kept = 0;
-        for (int q = b0; q < b0 + kCountsWarps && q < nowned; ++q) chunk_kept += s_kept[q];
-        rank_before += chunk_kept;
-        if (s >= nowned || !s_kept[s]) continue;
-        const long long o = base + my_rank;
+    for (int s = warp; s < nowned; s += kCountsWarps) {
+        if (!s_kept[s]) continue;
+        const long long o = base + (long long)s_rank[s];
         const int a = s_seg[s], b = s_seg[s + 1];
         for (int i = lane; i < 2 * R; i += 32) dk[i] = 0;
         __syncwarp();
@@ -301,12 +404,8 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
             if (zabs > P) continue;
             const bool rev = s_rev[r] != 0;
             const int slot = rev ? P + zabs - 1 : zabs - 1;
-            const int c0 = rev ? sr0 : sf0;
-            uint32_t nn = 0;
-#pragma unroll
-            for (int oo = 0; oo < 4; ++oo) nn += s_cnt[(size_t)(c0 + oo) * cap + r];
             atomicAdd(&dk[slot], s_cnt[(size_t)(rev ? skr : skf) * cap + r]);
-            atomicAdd(&dN[slot], nn);
+            atomicAdd(&dN[slot], rev ? o_nr[r] : o_nf[r]);
         }
         __syncwarp();
         if (p.out_k) for (int i = lane; i < R; i += 32) p.out_k[o * R + i] = dk[i];
