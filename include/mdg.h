@@ -191,7 +191,9 @@ void mdg_fit_config_default(mdg_fit_config* cfg);
  * 1-indexed position z (counts.py:117-129), y_sum_total broadcast to the TaxID's rows
  * (counts.py:179-204) and the cut flag (counts.py:207-209; rows with |z| > max_position are
  * not kept and do not contribute to y_sum_total).
- * Per-TaxID outputs (capacity n_rows entries is always enough; kept TaxIDs in input order):
+ * Per-TaxID outputs (the caller provides room for out_capacity TaxIDs; the number of runs of
+ * equal tax_id in the input is always enough; kept TaxIDs come out in input order; a too small
+ * capacity is an MDG_ERR_INVALID error, nothing is written past it):
  * tax id, N_alignments, first row index, dense k(z)/N(z) as [n_tax][2*max_position] with
  * slot z-1 for z>0 and max_position+|z|-1 for z<0, summed over the TaxID's rows at that z;
  * optional out_noise [n_tax][3] (normalized_noise, _forward, _reverse of fits.py:359-376, over the
@@ -210,7 +212,7 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows,
                       int8_t* z_row, uint64_t* y_sum_total_row, uint8_t* keep_row,
                       int64_t* out_tax_id, uint32_t* out_n_alignments, int64_t* out_first_row,
                       uint32_t* out_k, uint32_t* out_N, double* out_noise,
-                      int64_t* out_n_tax /* host pointer */);
+                      int64_t out_capacity, int64_t* out_n_tax /* host pointer */);
 
 /*
  * K3-K7 — fit a dense batch of TaxIDs. Replaces fits.py:428-469 for every TaxID.

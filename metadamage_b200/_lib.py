@@ -63,7 +63,7 @@ def load():
     lib.mdg_fit_config_default.argtypes = [C.POINTER(FitConfig)]
     lib.mdg_fit_config_default.restype = None
     lib.mdg_counts_reduce.argtypes = (
-        [vp, i32, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, u32, u64] + [vp] * 13 + [C.POINTER(i64)]
+        [vp, i32, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, u32, u64] + [vp] * 13 + [i64, C.POINTER(i64)]
     )
     lib.mdg_fit_batch.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, C.POINTER(FitConfig)] + [vp] * 7
     lib.mdg_test_lgamma_digamma.argtypes = [vp, i64, vp, vp, vp]

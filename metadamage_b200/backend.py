@@ -89,6 +89,8 @@ class Context:
             raise ValueError("counts16 must be [16][n_rows] (ref-major ACGT x ACGT)")
         fr, fo = _base_index(fwd)
         rr, ro = _base_index(rev)
+        # room for every run of equal tax_id (an upper bound of the kept TaxIDs)
+        m_cap = int(np.count_nonzero(tax_id[1:] != tax_id[:-1])) + 1 if n else 0
         out = {}
         if want_rows:
             out.update(
@@ -97,9 +99,9 @@ class Context:
                 z=np.empty(n, np.int8), y_sum_total=np.empty(n, np.uint64), keep=np.empty(n, np.uint8),
             )
         out.update(
-            tax_id=np.empty(n, np.int64), n_alignments=np.empty(n, np.uint32), first_row=np.empty(n, np.int64),
-            k=np.empty((n, 2 * P), np.uint32), N=np.empty((n, 2 * P), np.uint32),
-            noise=np.empty((n, 3), np.float64) if want_noise else None,
+            tax_id=np.empty(m_cap, np.int64), n_alignments=np.empty(m_cap, np.uint32), first_row=np.empty(m_cap, np.int64),
+            k=np.empty((m_cap, 2 * P), np.uint32), N=np.empty((m_cap, 2 * P), np.uint32),
+            noise=np.empty((m_cap, 3), np.float64) if want_noise else None,
         )
         n_tax = C.c_int64(0)
         g = out.get
@@ -108,7 +110,7 @@ class Context:
             fr, fo, rr, ro, P, int(min_alignments), int(min_y_sum),
             ptr(g("n_fwd_ref")), ptr(g("n_rev_ref")), ptr(g("f_fwd")), ptr(g("f_rev")), ptr(g("z")),
             ptr(g("y_sum_total")), ptr(g("keep")), ptr(out["tax_id"]), ptr(out["n_alignments"]),
-            ptr(out["first_row"]), ptr(out["k"]), ptr(out["N"]), ptr(out["noise"]), C.byref(n_tax)))
+            ptr(out["first_row"]), ptr(out["k"]), ptr(out["N"]), ptr(out["noise"]), m_cap, C.byref(n_tax)))
         m = n_tax.value
         for key in ("tax_id", "n_alignments", "first_row", "k", "N", "noise"):
             if out[key] is not None:
@@ -131,7 +133,7 @@ class Context:
             _dptr(cols["pos0"]), _dptr(cols["counts16"]), cols["counts16"].stride(0),
             fr, fo, rr, ro, int(max_position), int(min_alignments), int(min_y_sum),
             g("n_fwd_ref"), g("n_rev_ref"), g("f_fwd"), g("f_rev"), g("z"), g("y_sum_total"), g("keep"),
-            g("tax_id"), g("n_alignments"), g("first_row"), g("k"), g("N"), g("noise"), C.byref(n_tax)))
+            g("tax_id"), g("n_alignments"), g("first_row"), g("k"), g("N"), g("noise"), int(outs["k"].shape[0]), C.byref(n_tax)))
         return n_tax.value
 
     # ------------------------------------------------------------------ K3-K7

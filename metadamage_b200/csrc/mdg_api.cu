@@ -286,9 +286,9 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
                       uint32_t min_alignments, uint64_t min_y_sum, uint32_t* n_fwd_ref_row, uint32_t* n_rev_ref_row,
                       float* f_fwd_row, float* f_rev_row, int8_t* z_row, uint64_t* y_sum_total_row,
                       uint8_t* keep_row, int64_t* out_tax_id, uint32_t* out_n_alignments, int64_t* out_first_row,
-                      uint32_t* out_k, uint32_t* out_N, double* out_noise, int64_t* out_n_tax) {
+                      uint32_t* out_k, uint32_t* out_N, double* out_noise, int64_t out_capacity, int64_t* out_n_tax) {
     if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
-    if (n_rows < 0 || !out_n_tax || max_position < 1 || max_position > MDG_MAX_POSITION || fwd_ref < 0 || fwd_ref > 3 ||
+    if (n_rows < 0 || !out_n_tax || out_capacity < 0 || max_position < 1 || max_position > MDG_MAX_POSITION || fwd_ref < 0 || fwd_ref > 3 ||
         fwd_obs < 0 || fwd_obs > 3 || rev_ref < 0 || rev_ref > 3 || rev_obs < 0 || rev_obs > 3 ||
         (mem != MDG_HOST && mem != MDG_DEVICE) || counts_stride < n_rows) {
         set_error("mdg_counts_reduce: invalid argument");
@@ -336,7 +336,8 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
         cl.counts16 = dcounts;
         cl.stride = (long long)col_stride;
         MDG_CUDA_TRY(cudaGetLastError());
-        size_t out_bytes = n * (4 + 4 + 4 + 4 + 1 + 8 + 1 + 8 + 4 + 8) + n * (size_t)R * 8 + n * 24 + 256 * 16;
+        const size_t ncap = (size_t)out_capacity;
+        size_t out_bytes = n * (4 + 4 + 4 + 4 + 1 + 8 + 1) + ncap * (8 + 4 + 8) + ncap * (size_t)R * 8 + ncap * 24 + 256 * 16;
         rc = ctx->buf[1].ensure(out_bytes);
         if (rc) return rc;
         unsigned char* ob = ctx->buf[1].as<unsigned char>();
@@ -355,12 +356,12 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
         cl.z_row = (int8_t*)take(z_row, 1, n, false);
         cl.y_row = (unsigned long long*)take(y_sum_total_row, 8, n, false);
         cl.keep_row = (uint8_t*)take(keep_row, 1, n, false);
-        cl.out_tax = (long long*)take(out_tax_id, 8, n, true);
-        cl.out_nal = (uint32_t*)take(out_n_alignments, 4, n, true);
-        cl.out_first = (long long*)take(out_first_row, 8, n, true);
-        cl.out_k = (uint32_t*)take(out_k, 4 * (size_t)R, n, true);
-        cl.out_N = (uint32_t*)take(out_N, 4 * (size_t)R, n, true);
-        cl.out_noise = (double*)take(out_noise, 24, n, true);
+        cl.out_tax = (long long*)take(out_tax_id, 8, ncap, true);
+        cl.out_nal = (uint32_t*)take(out_n_alignments, 4, ncap, true);
+        cl.out_first = (long long*)take(out_first_row, 8, ncap, true);
+        cl.out_k = (uint32_t*)take(out_k, 4 * (size_t)R, ncap, true);
+        cl.out_N = (uint32_t*)take(out_N, 4 * (size_t)R, ncap, true);
+        cl.out_noise = (double*)take(out_noise, 24, ncap, true);
     } else {
         cl.tax_id = (const long long*)tax_id; cl.n_align = n_alignments; cl.is_rev = is_reverse; cl.pos0 = pos0;
         cl.counts16 = counts16; cl.stride = counts_stride;
@@ -413,20 +414,47 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
             return MDG_ERR_SEGMENT_TOO_LONG;
         }
         const long long n_tiles = (n_rows + cl.T - 1) / cl.T;
-        rc = ctx->buf[3].ensure((size_t)n_tiles * 8);
+        // per-tile block bookkeeping + temporaries for the (unordered) dense rows
+        const size_t ncap_t = (size_t)out_capacity;
+        rc = ctx->buf[3].ensure((size_t)n_tiles * (8 + 8 + 4) + 64);
         if (rc) return rc;
-        cl.tile_state = ctx->buf[3].as<unsigned long long>();
-        cl.tile_ticket = d_ticket;
-        cl.n_tax_out = d_ntax;
-        cl.error_flag = d_err;
+        long long* d_tile_base = ctx->buf[3].as<long long>();
+        long long* d_final_base = d_tile_base + n_tiles;
+        int* d_tile_cnt = reinterpret_cast<int*>(d_final_base + n_tiles);
+        const size_t tmp_bytes = ncap_t * (8 + 4 + 8 + 24 + (size_t)R * 8) + 256 * 8;
+        rc = ctx->buf[21].ensure(tmp_bytes);
+        if (rc) return rc;
+        unsigned char* tb = ctx->buf[21].as<unsigned char>();
+        size_t to = 0;
+        auto tmp = [&](size_t bytes) { void* q = tb + to; to += (bytes + 255) & ~(size_t)255; return q; };
+        CountsPermute cp = {};
+        cp.n_tiles = n_tiles; cp.tile_base = d_tile_base; cp.final_base = d_final_base; cp.tile_cnt = d_tile_cnt; cp.R = R;
+        cp.out_tax = cl.out_tax; cp.out_nal = cl.out_nal; cp.out_first = cl.out_first; cp.out_k = cl.out_k; cp.out_N = cl.out_N;
+        cp.out_noise = cl.out_noise;
+        CountsLaunch kl = cl;  // the tile kernel writes the per-TaxID rows into the temporaries
+        if (cl.out_tax) { cp.t_tax = (long long*)tmp(ncap_t * 8); kl.out_tax = (long long*)cp.t_tax; }
+        if (cl.out_nal) { cp.t_nal = (uint32_t*)tmp(ncap_t * 4); kl.out_nal = (uint32_t*)cp.t_nal; }
+        if (cl.out_first) { cp.t_first = (long long*)tmp(ncap_t * 8); kl.out_first = (long long*)cp.t_first; }
+        if (cl.out_k) { cp.t_k = (uint32_t*)tmp(ncap_t * R * 4); kl.out_k = (uint32_t*)cp.t_k; }
+        if (cl.out_N) { cp.t_N = (uint32_t*)tmp(ncap_t * R * 4); kl.out_N = (uint32_t*)cp.t_N; }
+        if (cl.out_noise) { cp.t_noise = (double*)tmp(ncap_t * 24); kl.out_noise = (double*)cp.t_noise; }
+        kl.tile_ticket = d_ticket;
+        kl.kept_counter = reinterpret_cast<unsigned long long*>(d_ntax + 3);
+        kl.tile_base = d_tile_base;
+        kl.tile_cnt = d_tile_cnt;
+        kl.capacity = out_capacity;
+        kl.error_flag = d_err;
         MDG_CUDA_TRY(cudaMemsetAsync(d_ntax, 0, 64, st));
-        MDG_CUDA_TRY(cudaMemsetAsync(cl.tile_state, 0, (size_t)n_tiles * 8, st));
         MDG_CUDA_TRY(cudaFuncSetAttribute(counts_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MDG_CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-        counts_reduce_kernel<<<(unsigned)n_tiles, kCountsThreads, smem, st>>>(cl);
+        counts_reduce_kernel<<<(unsigned)n_tiles, kCountsThreads, smem, st>>>(kl);
+        MDG_CUDA_TRY(cudaGetLastError());
+        counts_scan_kernel<<<1, 1024, 0, st>>>(d_tile_cnt, n_tiles, d_final_base, d_ntax);
+        MDG_CUDA_TRY(cudaGetLastError());
+        counts_permute_kernel<<<(unsigned)std::min<long long>(n_tiles, 4LL * ctx->num_sms * 4), 128, 0, st>>>(cp);
         MDG_CUDA_TRY(cudaGetLastError());
         MDG_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-        ctx->timings.n_launches++;
+        ctx->timings.n_launches += 3;
         MDG_CUDA_TRY(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
         MDG_CUDA_TRY(cudaMemcpyAsync(&h_ntax, d_ntax, sizeof(long long), cudaMemcpyDeviceToHost, st));
         MDG_CUDA_TRY(cudaStreamSynchronize(st));
@@ -435,6 +463,11 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
     if (h_err == CE_SEGMENT_TOO_LONG) {
         set_error("mdg_counts_reduce: a TaxID has more than %d rows (rows must be grouped by tax_id)", MDG_MAX_SEGMENT_ROWS);
         return MDG_ERR_SEGMENT_TOO_LONG;
+    }
+    if (h_err == CE_CAPACITY) {
+        set_error("mdg_counts_reduce: out_capacity (%lld) is smaller than the number of kept TaxIDs (%lld)",
+                  (long long)out_capacity, h_ntax);
+        return MDG_ERR_INVALID;
     }
     if (h_err == CE_OVERFLOW) {
         set_error("mdg_counts_reduce: a reference-base row sum exceeds uint32 (utils.py:338-339)");

@@ -8,11 +8,14 @@
 //   * one CTA per tile of T rows plus an L-row lookahead; the tile's SoA column chunks come into
 //     shared memory through 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) on one mbarrier;
 //   * the CTA owns every TaxID whose first row lies in [row0, row0+T): no carry crosses tiles,
-//     the only inter-CTA traffic is a warp-wide decoupled look-back on the count of kept TaxIDs
-//     (stable compaction of the dense output);
+//     the only inter-CTA traffic is ONE atomicAdd per tile that reserves the tile's block of dense
+//     output rows; a one-CTA scan and a block-permute kernel then put the blocks into input order
+//     (a decoupled look-back was measured to stall 28-42 % of the warp samples: with 448-row tiles
+//     the inclusive prefix cannot propagate as fast as tiles retire);
 //   * per-row work is vectorised: one thread handles 4 consecutive rows with 128-bit shared
-//     loads, results are staged in shared memory and leave with 128-bit coalesced global stores
-//     (tile starts are 16-byte aligned for every column type);
+//     loads and writes the row-local outputs (reference sums, error rates, z) of the tile's
+//     nominal rows straight from registers with 128-bit stores (tile starts are 16-byte aligned
+//     for every column type); y_sum_total and the cut flag follow once the TaxID sums are known;
 //   * per-TaxID sums are a short serial loop of one thread per TaxID over staged values; the
 //     dense k/N (and the optional noise) of KEPT TaxIDs use one warp per TaxID, lane = row.
 // The first version (one warp per TaxID for everything) was instruction-issue bound at 30 warp
@@ -25,9 +28,9 @@ namespace mdg {
 constexpr int kCountsThreads = 128;
 constexpr int kCountsWarps = kCountsThreads / 32;
 // shared bytes per staged row, without the count columns (4 bytes per staged column on top)
-constexpr int kCountsBytesPerRow = 8 + 4 + 1 + 1 + 16 + 4 + 1 + 1 + 4 + 8 + 1;
+constexpr int kCountsBytesPerRow = 8 + 4 + 1 + 1 + 8 + 4 + 1 + 1 + 4 + 8 + 1;
 
-enum CountsError : int { CE_NONE = 0, CE_SEGMENT_TOO_LONG = 1, CE_OVERFLOW = 2 };
+enum CountsError : int { CE_NONE = 0, CE_SEGMENT_TOO_LONG = 1, CE_OVERFLOW = 2, CE_CAPACITY = 3 };
 
 struct CountsLaunch {
     long long n_rows;
@@ -64,8 +67,10 @@ struct CountsLaunch {
     int use_tma;            // all column bases 16-byte aligned
     int vec_out;            // per-row output bases 16-byte aligned -> 128-bit stores
     unsigned int* tile_ticket;
-    unsigned long long* tile_state;  // decoupled look-back: flag << 62 | value
-    long long* n_tax_out;            // device scalar
+    unsigned long long* kept_counter;  // device scalar: dense rows reserved so far (unordered, one atomicAdd per tile)
+    long long* tile_base;              // [n_tiles] start of the tile's block in the temporary dense arrays
+    int* tile_cnt;                     // [n_tiles] kept TaxIDs of the tile
+    long long capacity;                // rows available in the per-TaxID arrays
     int* error_flag;
 };
 
@@ -98,9 +103,7 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
     uint32_t* s_nal = s_cnt + (size_t)p.ncols * cap;
     uint32_t* o_nf = s_nal + cap;
     uint32_t* o_nr = o_nf + cap;
-    float* o_ff = reinterpret_cast<float*>(o_nr + cap);
-    float* o_fr = o_ff + cap;
-    uint32_t* o_yc = reinterpret_cast<uint32_t*>(o_fr + cap);   // y contribution of the row; later: rank of the segment
+    uint32_t* o_yc = o_nr + cap;                                // y contribution of the row; later: rank of the segment
     int* s_seg = reinterpret_cast<int*>(o_yc + cap);            // head row of segment s; s_seg[nseg] = nload
     unsigned long long* s_ysum = reinterpret_cast<unsigned long long*>(s_seg + cap + 4);
     uint8_t* s_rev = reinterpret_cast<uint8_t*>(s_ysum + cap);
@@ -226,11 +229,28 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
             if (ovf) atomicMax(p.error_flag, (int)CE_OVERFLOW);
             *reinterpret_cast<uint4*>(o_nf + i0) = make_uint4(nf[0], nf[1], nf[2], nf[3]);
             *reinterpret_cast<uint4*>(o_nr + i0) = make_uint4(nr[0], nr[1], nr[2], nr[3]);
-            *reinterpret_cast<float4*>(o_ff + i0) = make_float4(ff[0], ff[1], ff[2], ff[3]);
-            *reinterpret_cast<float4*>(o_fr + i0) = make_float4(fr[0], fr[1], fr[2], fr[3]);
             *reinterpret_cast<uint4*>(o_yc + i0) = make_uint4(yc[0], yc[1], yc[2], yc[3]);
             *reinterpret_cast<uint32_t*>(o_z + i0) = zpack;
             *reinterpret_cast<uint32_t*>(o_head + i0) = headbits;
+            // row-local outputs of the tile's nominal rows [0, nown): every row has exactly one nominal tile
+            const long long gi = row0 + i0;
+            if (p.vec_out && i0 + 4 <= nown) {
+                if (p.n_fwd_row) *reinterpret_cast<uint4*>(p.n_fwd_row + gi) = make_uint4(nf[0], nf[1], nf[2], nf[3]);
+                if (p.n_rev_row) *reinterpret_cast<uint4*>(p.n_rev_row + gi) = make_uint4(nr[0], nr[1], nr[2], nr[3]);
+                if (p.f_fwd_row) *reinterpret_cast<float4*>(p.f_fwd_row + gi) = make_float4(ff[0], ff[1], ff[2], ff[3]);
+                if (p.f_rev_row) *reinterpret_cast<float4*>(p.f_rev_row + gi) = make_float4(fr[0], fr[1], fr[2], fr[3]);
+                if (p.z_row) *reinterpret_cast<uint32_t*>(p.z_row + gi) = zpack;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (i0 + j >= nown) continue;
+                    if (p.n_fwd_row) p.n_fwd_row[gi + j] = nf[j];
+                    if (p.n_rev_row) p.n_rev_row[gi + j] = nr[j];
+                    if (p.f_fwd_row) p.f_fwd_row[gi + j] = ff[j];
+                    if (p.f_rev_row) p.f_rev_row[gi + j] = fr[j];
+                    if (p.z_row) p.z_row[gi + j] = (int8_t)((zpack >> (8 * j)) & 0xffu);
+                }
+            }
         }
         // ordered compaction of the head rows: warp scan + block offsets
         int incl = nheads;
@@ -292,17 +312,17 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
         }
         if (lane == 0) {
             s_kept_total = running;
-            if (tile > 0) {
-                volatile unsigned long long* st = p.tile_state;
-                st[tile] = (1ull << 62) | (unsigned long long)running;
-                __threadfence();
-            }
+            const long long base = running ? (long long)atomicAdd(p.kept_counter, (unsigned long long)running) : 0;
+            s_base = base;
+            p.tile_base[tile] = base;
+            p.tile_cnt[tile] = running;
+            if (base + running > p.capacity) atomicMax(p.error_flag, (int)CE_CAPACITY);
         }
         __syncwarp();
     }
 
-    // ---------------- phase 4: per-row outputs of the owned rows, 128-bit coalesced ----------------
-    if (nowned > 0) {
+    // ---------------- phase 4: y_sum_total and the cut flag of the owned rows ----------------
+    if (nowned > 0 && (p.y_row || p.keep_row)) {
         const int a0 = s_seg[0], a1 = s_seg[nowned];
         for (int g = tid + (a0 >> 2); g < ((a1 + 3) >> 2); g += kCountsThreads) {
             const int i0 = g << 2;
@@ -329,63 +349,23 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
             }
             const long long gi = row0 + i0;
             if (p.vec_out && i0 >= a0 && i0 + 4 <= a1) {
-                if (p.n_fwd_row) *reinterpret_cast<uint4*>(p.n_fwd_row + gi) = *reinterpret_cast<const uint4*>(o_nf + i0);
-                if (p.n_rev_row) *reinterpret_cast<uint4*>(p.n_rev_row + gi) = *reinterpret_cast<const uint4*>(o_nr + i0);
-                if (p.f_fwd_row) *reinterpret_cast<float4*>(p.f_fwd_row + gi) = *reinterpret_cast<const float4*>(o_ff + i0);
-                if (p.f_rev_row) *reinterpret_cast<float4*>(p.f_rev_row + gi) = *reinterpret_cast<const float4*>(o_fr + i0);
                 if (p.y_row) {
                     *reinterpret_cast<ulonglong2*>(p.y_row + gi) = make_ulonglong2(y[0], y[1]);
                     *reinterpret_cast<ulonglong2*>(p.y_row + gi + 2) = make_ulonglong2(y[2], y[3]);
                 }
-                if (p.z_row) *reinterpret_cast<uint32_t*>(p.z_row + gi) = zpack;
                 if (p.keep_row) *reinterpret_cast<uint32_t*>(p.keep_row + gi) = keeppack;
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int i = i0 + j;
                     if (i < a0 || i >= a1) continue;
-                    if (p.n_fwd_row) p.n_fwd_row[gi + j] = o_nf[i];
-                    if (p.n_rev_row) p.n_rev_row[gi + j] = o_nr[i];
-                    if (p.f_fwd_row) p.f_fwd_row[gi + j] = o_ff[i];
-                    if (p.f_rev_row) p.f_rev_row[gi + j] = o_fr[i];
                     if (p.y_row) p.y_row[gi + j] = y[j];
-                    if (p.z_row) p.z_row[gi + j] = (int8_t)((zpack >> (8 * j)) & 0xffu);
                     if (p.keep_row) p.keep_row[gi + j] = (uint8_t)((keeppack >> (8 * j)) & 1u);
                 }
             }
         }
     }
 
-    // ---------------- phase 5 (warp 0): decoupled look-back, 32 predecessor tiles at a time ----------------
-    if (warp == 0) {
-        const unsigned long long VMASK = (1ull << 62) - 1;
-        volatile unsigned long long* st = p.tile_state;
-        const int running = s_kept_total;
-        long long excl = 0;
-        if (tile > 0) {
-            long long hi = (long long)tile - 1;
-            for (;;) {
-                const long long t = hi - lane;
-                unsigned long long v = 2ull << 62;  // tiles before 0 act as an inclusive prefix of 0
-                if (t >= 0) { do { v = st[t]; } while ((v >> 62) == 0ull); }
-                const unsigned inc_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-                const int stop = inc_mask ? __ffs(inc_mask) - 1 : 31;  // nearest inclusive prefix
-                long long contrib = (lane <= stop) ? (long long)(v & VMASK) : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                excl += contrib;
-                if (inc_mask) break;
-                hi -= 32;
-            }
-        }
-        if (lane == 0) {
-            st[tile] = (2ull << 62) | (unsigned long long)(excl + running);
-            __threadfence();
-            s_base = excl;
-            // only the LAST tile publishes the total (an earlier tile's lookahead can also reach the end of the data)
-            if (row0 + p.T >= p.n_rows && p.n_tax_out) *p.n_tax_out = excl + running;
-        }
-    }
     __syncthreads();
     const long long base = s_base;
     if (s_kept_total == 0) return;
@@ -396,6 +376,7 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
     for (int s = warp; s < nowned; s += kCountsWarps) {
         if (!s_kept[s]) continue;
         const long long o = base + (long long)s_rank[s];
+        if (o >= p.capacity) continue;
         const int a = s_seg[s], b = s_seg[s + 1];
         for (int i = lane; i < 2 * R; i += 32) dk[i] = 0;
         __syncwarp();
@@ -471,6 +452,62 @@ __global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const Cou
             }
         }
         __syncwarp();
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// K1b: exclusive scan of the per-tile kept counts (one CTA) -> final block starts and the total
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) counts_scan_kernel(const int* __restrict__ tile_cnt, long long n_tiles,
+                                                           long long* __restrict__ final_base, long long* __restrict__ n_tax_out) {
+    __shared__ long long s_part[1024];
+    const int tid = threadIdx.x;
+    const long long per = (n_tiles + 1023) / 1024;
+    const long long lo = (long long)tid * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    long long sum = 0;
+    for (long long t = lo; t < hi; ++t) sum += tile_cnt[t];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const long long v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    long long run = s_part[tid] - sum;
+    for (long long t = lo; t < hi; ++t) { final_base[t] = run; run += tile_cnt[t]; }
+    if (tid == 1023) *n_tax_out = s_part[1023];
+}
+
+// K1c: move every tile's block of per-TaxID rows from its reserved (unordered) place to input order
+struct CountsPermute {
+    long long n_tiles;
+    const long long* tile_base;
+    const long long* final_base;
+    const int* tile_cnt;
+    int R;
+    const long long* t_tax; long long* out_tax;
+    const uint32_t* t_nal; uint32_t* out_nal;
+    const long long* t_first; long long* out_first;
+    const uint32_t* t_k; uint32_t* out_k;
+    const uint32_t* t_N; uint32_t* out_N;
+    const double* t_noise; double* out_noise;
+};
+
+__global__ void __launch_bounds__(128) counts_permute_kernel(const CountsPermute p) {
+    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int cnt = p.tile_cnt[t];
+        if (cnt == 0) continue;
+        const long long src = p.tile_base[t], dst = p.final_base[t];
+        const int tid = threadIdx.x;
+        if (p.out_tax) for (int i = tid; i < cnt; i += 128) p.out_tax[dst + i] = p.t_tax[src + i];
+        if (p.out_nal) for (int i = tid; i < cnt; i += 128) p.out_nal[dst + i] = p.t_nal[src + i];
+        if (p.out_first) for (int i = tid; i < cnt; i += 128) p.out_first[dst + i] = p.t_first[src + i];
+        const long long nR = (long long)cnt * p.R;
+        if (p.out_k) for (long long i = tid; i < nR; i += 128) p.out_k[dst * p.R + i] = p.t_k[src * p.R + i];
+        if (p.out_N) for (long long i = tid; i < nR; i += 128) p.out_N[dst * p.R + i] = p.t_N[src * p.R + i];
+        if (p.out_noise) for (int i = tid; i < 3 * cnt; i += 128) p.out_noise[dst * 3 + i] = p.t_noise[src * 3 + i];
     }
 }
 
