@@ -6,7 +6,7 @@ import os
 from ._abi import FitConfig, Timings
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdgb200.so")
+LIB_PATH = os.environ.get("MDG_LIB_PATH") or os.path.join(_HERE, "libmdgb200.so")  # override: kernel A/B experiments
 
 # every symbol include/mdg.h declares
 EXPORTED_SYMBOLS = (

@@ -19,6 +19,9 @@ HEADERS = [
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    # no implicit mul+add contraction: every kernel variant (warp / half-warp groups, 1-4 positions
+    # per lane) must give bit-identical results; fused operations are written as fma() explicitly
+    "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
 ]
 

@@ -747,13 +747,12 @@ __global__ void test_logp_kernel(int P, const uint32_t* k, const uint32_t* N, Pr
     load_obs<NPL, 32>(ob, k, N, P, mask, lane);
     double logC[NPL];
     log_binom_coeff<NPL>(ob, logC);
-    const int n_obs = mask == 0 ? 2 * P : P;
     double uu[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) uu[j] = u[e * 4 + j];
     double logp, grad[D], ll[NPL];
     bool valid;
-    eval_model<MODEL, NPL, 32>(ob, uu, jac, pr, n_obs < NPL * 32, 0xffffffffu, lane, logp, grad, ll, valid);
+    eval_model<MODEL, NPL, 32>(ob, uu, jac, pr, (mask == 0 ? 2 * P : P) < NPL * 32, 0xffffffffu, lane, logp, grad, ll, valid);
     double sumC = 0.0;
 #pragma unroll
     for (int s = 0; s < NPL; ++s) sumC += logC[s];

@@ -6,6 +6,27 @@
 #include <math.h>
 #include "mdg.h"
 
+// A/B switches of the kernel tuning experiments (profiles/r01_nuts_tuning.md). Defaults = shipped.
+// Measured on B200, 10k TaxIDs, NUTS kernels only: LOGFN 1 -10 %, UNIFORM_SHIFT 1 +50 %,
+// COLD_INLINE 0 +3 %, EVAL_LOOP 1 +20 %.
+#ifndef MDG_LOGFN
+#define MDG_LOGFN 1          // 1: log_pos (constant-bank coefficients); 0: CUDA log()
+#endif
+#ifndef MDG_COLD_INLINE
+#define MDG_COLD_INLINE 1    // 1: everything inlined; 0: cold helpers (Philox, Box-Muller, logaddexp, ...) out of line
+#endif
+#ifndef MDG_UNIFORM_SHIFT
+#define MDG_UNIFORM_SHIFT 0  // 0: small-argument shift under a per-lane branch; 1: under a group-uniform branch
+#endif
+#ifndef MDG_EVAL_LOOP
+#define MDG_EVAL_LOOP 0      // 1: the five lgamma/digamma evaluations as a rolled loop (small I-cache footprint)
+#endif
+#if MDG_COLD_INLINE
+#define MDG_COLD __forceinline__
+#else
+#define MDG_COLD __noinline__
+#endif
+
 namespace mdg {
 
 // ---------------------------------------------------------------------------------------------
@@ -40,7 +61,7 @@ __host__ __device__ __forceinline__ uint2 make_key(uint64_t seed, int64_t tax_id
     return make_uint2((uint32_t)k, (uint32_t)(k >> 32));
 }
 
-__device__ __forceinline__ uint4 philox4x32(uint2 key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+__device__ MDG_COLD uint4 philox4x32(uint2 key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
     uint32_t k0 = key.x, k1 = key.y;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -61,17 +82,6 @@ __device__ __forceinline__ uint32_t c2word(int run_kind, uint32_t purpose) {
 __device__ __forceinline__ void uniform2(uint4 o, double& u0, double& u1) {
     u0 = ((double)(o.x >> 5) * 67108864.0 + (double)(o.y >> 6) + 0.5) * (1.0 / 9007199254740992.0);
     u1 = ((double)(o.z >> 5) * 67108864.0 + (double)(o.w >> 6) + 0.5) * (1.0 / 9007199254740992.0);
-}
-
-// two standard normals (Box-Muller)
-__device__ __forceinline__ void normal2(uint4 o, double& n0, double& n1) {
-    double u0, u1;
-    uniform2(o, u0, u1);
-    double rad = sqrt(-2.0 * log(u0));
-    double s, c;
-    sincos(6.283185307179586476925 * u1, &s, &c);
-    n0 = rad * c;
-    n1 = rad * s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -98,41 +108,148 @@ __device__ __forceinline__ unsigned group_mask() {
 // FP64 special functions
 // ---------------------------------------------------------------------------------------------
 
-// lgamma(x) and digamma(x) for x > 0 in one pass. x < 10 is shifted to y = x + 10 with the
-// product P = x(x+1)...(x+9) and its derivative P' (so that lgamma(x) = lgamma(y) - log P and
-// digamma(x) = digamma(y) - P'/P: one log and one division instead of ten); y >= 10 uses the
-// Stirling / asymptotic series with 7 Bernoulli terms (truncation < 4e-17 absolute at y = 10).
+
+
+// ---------------------------------------------------------------------------------------------
+// Fast path special functions of the fit kernels. Coefficients live in constant memory so that
+// the FP64 instructions read them as c[bank][offset] operands (ncu on the first version showed
+// 31 % of all issued instructions were moves materialising FP64 literals).
+// ---------------------------------------------------------------------------------------------
+__constant__ double kLogCoef[9] = {
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
+    6.93147180369123816490e-01, 1.90821492927058770002e-10};
+// Stirling series of lgamma: 1/12, 1/360, 1/1260, 1/1680, 1/1188, 691/360360, 1/156 (alternating signs)
+__constant__ double kStirLg[7] = {1.0 / 12.0, 1.0 / 360.0, 1.0 / 1260.0, 1.0 / 1680.0, 1.0 / 1188.0, 691.0 / 360360.0, 1.0 / 156.0};
+// asymptotic series of digamma: 1/12, 1/120, 1/252, 1/240, 1/132, 691/32760, 1/12
+__constant__ double kStirDg[7] = {1.0 / 12.0, 1.0 / 120.0, 1.0 / 252.0, 1.0 / 240.0, 1.0 / 132.0, 691.0 / 32760.0, 1.0 / 12.0};
+
+// natural log of a positive, normal, finite double (fdlibm's kernel, < 1 ulp); no special cases
+__device__ __forceinline__ double log_pos(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int adj = (hi + 0x95f64) & 0x100000;  // mantissa into [sqrt(1/2), sqrt(2))
+    hi |= adj ^ 0x3ff00000;
+    e += adj >> 20;
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, kLogCoef[5], kLogCoef[3]), kLogCoef[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, kLogCoef[6], kLogCoef[4]), kLogCoef[2]), kLogCoef[0]);
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)e;
+    return fma(dk, kLogCoef[7], -((hfsq - fma(s, hfsq + (t1 + t2), dk * kLogCoef[8])) - f));
+}
+
+// two standard normals (Box-Muller); sincospi needs no large-argument reduction
+__device__ __forceinline__ void normal2(uint4 o, double& n0, double& n1) {
+    double u0, u1;
+    uniform2(o, u0, u1);
+    const double rad = sqrt(-2.0 * log_pos(u0));
+    double s, c;
+    sincospi(2.0 * u1, &s, &c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+
+// Out-of-line copies of the transcendental functions for the COLD parts of the kernels (once per
+// transition or rarer). The NUTS kernel was instruction-fetch bound (ncu: stall_no_instruction
+// 45 % of all stalls with 12.4k SASS instructions); one shared copy of each keeps the hot loop
+// (one gradient evaluation + leaf bookkeeping) inside the instruction caches.
+__device__ MDG_COLD double exp_cold(double x) { return exp(x); }
+__device__ MDG_COLD double log_cold(double x) { return log(x); }
+__device__ MDG_COLD double sigmoid_cold(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// st = lgamma(y) - 0.5 log(2 pi) and dg = digamma(y) for y >= 10 (7 Bernoulli terms each)
+__device__ __forceinline__ double log_sel(double x) {
+#if MDG_LOGFN
+    return log_pos(x);
+#else
+    return log(x);
+#endif
+}
+
+__device__ __forceinline__ void stirling(double y, double& st, double& dg) {
+    const double L = log_sel(y);
+    const double t = 1.0 / y;
+    const double t2 = t * t;
+    double sl = fma(t2, -kStirLg[6], kStirLg[5]);
+    sl = fma(t2, -sl, kStirLg[4]);
+    sl = fma(t2, -sl, kStirLg[3]);
+    sl = fma(t2, -sl, kStirLg[2]);
+    sl = fma(t2, -sl, kStirLg[1]);
+    sl = fma(t2, -sl, kStirLg[0]);
+    double sd = fma(t2, -kStirDg[6], kStirDg[5]);
+    sd = fma(t2, -sd, kStirDg[4]);
+    sd = fma(t2, -sd, kStirDg[3]);
+    sd = fma(t2, -sd, kStirDg[2]);
+    sd = fma(t2, -sd, kStirDg[1]);
+    sd = fma(t2, -sd, kStirDg[0]);
+    st = fma(t, sl, fma(y - 0.5, L, -y));
+    dg = fma(-t2, sd, fma(-0.5, t, L));
+}
+
+// lgamma(x) and digamma(x), x > 0, in one pass. x < 10 is shifted to y = x + 10 with the product
+// P = x (x+1) ... (x+9) and its derivative P' (lgamma(x) = lgamma(y) - log P, digamma(x) =
+// digamma(y) - P'/P: one log and one division instead of ten); y >= 10 uses the Stirling /
+// asymptotic series with 7 Bernoulli terms (truncation < 4e-17 absolute at y = 10).
+__device__ __forceinline__ void lgam_digam_u(double x, unsigned gmask, double& lg, double& dg) {
+    double y = x, logP = 0.0, dP = 0.0;
+    const bool small = x < 10.0;
+#if MDG_UNIFORM_SHIFT
+    if (__any_sync(gmask, small)) {
+        double P = small ? x : 1.0, Q = small ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 1; i < 10; ++i) {
+            const double xi = small ? x + (double)i : 1.0;
+            Q = fma(Q, xi, small ? P : 0.0);
+            P *= xi;
+        }
+        logP = log_sel(P);
+        dP = Q / P;
+        y = small ? x + 10.0 : x;
+    }
+#else
+    if (small) {
+        double P = x, Q = 1.0;
+#pragma unroll
+        for (int i = 1; i < 10; ++i) {
+            const double xi = x + (double)i;
+            Q = fma(Q, xi, P);
+            P *= xi;
+        }
+        logP = log_sel(P);
+        dP = Q / P;
+        y = x + 10.0;
+    }
+#endif
+    double st, d;
+    stirling(y, st, d);
+    lg = (st + 0.91893853320467274178) - logP;
+    dg = d - dP;
+}
+
+// single-thread forms (log C(N,k), the predictive's BTRS sampler, the special-function test hook)
 __device__ __forceinline__ void lgam_digam(double x, double& lg, double& dg) {
     double y = x, logP = 0.0, dP = 0.0;
     if (x < 10.0) {
         double P = x, Q = 1.0;
 #pragma unroll
         for (int i = 1; i < 10; ++i) {
-            double xi = x + (double)i;
+            const double xi = x + (double)i;
             Q = fma(Q, xi, P);
             P *= xi;
         }
-        logP = log(P);
+        logP = log_sel(P);
         dP = Q / P;
         y = x + 10.0;
     }
-    double L = log(y);
-    double t = 1.0 / y;
-    double t2 = t * t;
-    double sl = fma(t2, -1.0 / 156.0, 691.0 / 360360.0);
-    sl = fma(t2, -sl, 1.0 / 1188.0);
-    sl = fma(t2, -sl, 1.0 / 1680.0);
-    sl = fma(t2, -sl, 1.0 / 1260.0);
-    sl = fma(t2, -sl, 1.0 / 360.0);
-    sl = fma(t2, -sl, 1.0 / 12.0);
-    double sd = fma(t2, -1.0 / 12.0, 691.0 / 32760.0);
-    sd = fma(t2, -sd, 1.0 / 132.0);
-    sd = fma(t2, -sd, 1.0 / 240.0);
-    sd = fma(t2, -sd, 1.0 / 252.0);
-    sd = fma(t2, -sd, 1.0 / 120.0);
-    sd = fma(t2, -sd, 1.0 / 12.0);
-    lg = fma(y - 0.5, L, -y) + 0.91893853320467274178 + t * sl - logP;
-    dg = L - 0.5 * t - t2 * sd - dP;
+    double st, d;
+    stirling(y, st, d);
+    lg = (st + 0.91893853320467274178) - logP;
+    dg = d - dP;
 }
 
 __device__ __forceinline__ double lgam(double x) {
@@ -150,10 +267,11 @@ __device__ __forceinline__ void softplus_sigmoid(double u, double& sp, double& s
     sg = (u >= 0.0) ? inv : e * inv;
 }
 
-__device__ __forceinline__ double logaddexp(double a, double b) {
+// log(e^a + e^b) = max + log(1 + e^-|a-b|); out of line (used twice per leaf, never in the gradient)
+__device__ MDG_COLD double logaddexp(double a, double b) {
     if (a == -INFINITY && b == -INFINITY) return -INFINITY;
-    double m = fmax(a, b);
-    return m + log(exp(a - m) + exp(b - m));
+    const double m = fmax(a, b), d = -fabs(a - b);
+    return isnan(d) ? (a + b) : m + log_pos(1.0 + exp(d));
 }
 
 }  // namespace mdg

@@ -81,23 +81,41 @@ __device__ __forceinline__ bool is_turning(const double (&imm)[D], const double*
     return (dl <= 0.0) || (dr <= 0.0);
 }
 
+struct Vec4 { double v[4]; };
+
+// momentum r ~ N(0, M) with M^-1 = diag(imm): out of line (one copy; Box-Muller + Philox are cold)
+template <int D>
+__device__ MDG_COLD Vec4 draw_momentum_cold(uint2 key, uint32_t c1, uint32_t c2, uint32_t c3, Vec4 imm) {
+    Vec4 r;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        double n0 = 0.0, n1 = 0.0;
+        if (2 * b < D) normal2(philox4x32(key, (uint32_t)b, c1, c2, c3), n0, n1);
+        r.v[2 * b] = 2 * b < D ? n0 / sqrt(imm.v[2 * b]) : 0.0;
+        r.v[2 * b + 1] = 2 * b + 1 < D ? n1 / sqrt(imm.v[2 * b + 1]) : 0.0;
+    }
+    return r;
+}
+
 template <int D>
 __device__ __forceinline__ void draw_momentum(uint2 key, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const double (&imm)[D], double (&r)[D]) {
+    Vec4 m;
 #pragma unroll
-    for (int b = 0; b < (D + 1) / 2; ++b) {
-        double n0, n1;
-        normal2(philox4x32(key, (uint32_t)b, c1, c2, c3), n0, n1);
-        r[2 * b] = n0 / sqrt(imm[2 * b]);
-        if (2 * b + 1 < D) r[2 * b + 1] = n1 / sqrt(imm[2 * b + 1]);
-    }
+    for (int j = 0; j < 4; ++j) m.v[j] = j < D ? imm[j] : 1.0;
+    const Vec4 out = draw_momentum_cold<D>(key, c1, c2, c3, m);
+#pragma unroll
+    for (int j = 0; j < D; ++j) r[j] = out.v[j];
 }
 
 // ---------------------------------------------------------------------------------------------
 // K4: NUTS. MODEL 0 = PMD, 1 = null. NPL positions per lane. GW lanes per chain.
 // ---------------------------------------------------------------------------------------------
+#ifndef MDG_NUTS_MINBLOCKS
+#define MDG_NUTS_MINBLOCKS 3
+#endif
 template <int MODEL, int NPL, int GW, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
+__global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(const FitLaunch p) {
     constexpr int D = ModelDim<MODEL>::value;
     constexpr int GROUPS = 32 / GW;
     __shared__ GroupShared<D> sh_all[WARPS * GROUPS];
@@ -109,7 +127,7 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
     GroupShared<D>& sh = sh_all[warp * GROUPS + grp];
     const int W = p.cfg.num_warmup, S = p.cfg.num_samples, P = p.P;
     const int max_depth = p.cfg.max_tree_depth < kMaxTreeDepth ? p.cfg.max_tree_depth : kMaxTreeDepth;
-    const double log_target_heur = log(0.8);
+    const double log_target_heur = -0.22314355131420976;  // log(0.8)
 
     for (;;) {
         if (lane == 0) sh_item[warp] = atomicAdd(p.work_counter, 1u);
@@ -121,8 +139,7 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
         if (GW == 32) { tax = (int)(item / (unsigned)p.n_masks); mask = p.mask0 + (int)(item % (unsigned)p.n_masks); }
         else { tax = (int)item; mask = 1 + grp; }
         const int run_kind = mask * 2 + MODEL;
-        const int n_obs = mask == 0 ? 2 * P : P;
-        const bool has_spare = n_obs < NPL * GW;
+        const bool has_spare = (mask == 0 ? 2 * P : P) < NPL * GW;
         const uint2 key = make_key(p.cfg.seed, p.tax_id[tax]);
 
         LaneObs<NPL> ob;
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
             return heur_try();
         };
         auto reset_dual_averaging = [&]() {
-            da_x = 0.0; da_xavg = 0.0; da_gavg = 0.0; da_t = 0; da_prox = log(10.0 * eps);
+            da_x = 0.0; da_xavg = 0.0; da_gavg = 0.0; da_t = 0; da_prox = log_cold(10.0 * eps);
         };
 
         init_candidate();
@@ -288,9 +305,13 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
                         // ---- _combine_tree(..., biased_transition=False) ----
                         double us, unused;
                         uniform2(philox4x32(key, leaf_counter, (uint32_t)t, c2word(run_kind, P_SUB), 0u), us, unused);
-                        double prob = 1.0 / (1.0 + exp(-(leaf_w - s_weight)));
+                        // expit(d) and logaddexp share one exponential: e = exp(-|d|)
+                        const double dlt = leaf_w - s_weight;
+                        const double ed = exp(-fabs(dlt));
+                        const double inv = 1.0 / (1.0 + ed);
+                        const double prob = dlt >= 0.0 ? inv : ed * inv;
                         take = us < prob;  // NaN -> false
-                        s_weight = logaddexp(s_weight, leaf_w);
+                        s_weight = isnan(dlt) ? -INFINITY : fmax(s_weight, leaf_w) + log_pos(1.0 + ed);
                         s_sum_acc += leaf_acc;
 #pragma unroll
                         for (int j = 0; j < D; ++j) s_rsum[j] += rn[j];
@@ -335,8 +356,9 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
                         for (int j = 0; j < D; ++j) { zf[j] = zn[j]; rf[j] = rn[j]; gf[j] = gn[j]; }
                     } else {
                         // ---- subtree finished: _combine_tree(..., biased_transition=True) ----
-                        double prob = exp(s_weight - m_weight);
-                        if (turning || s_div) prob = 0.0;
+                        const double dlt_m = s_weight - m_weight;
+                        const double pm = exp(dlt_m);
+                        const double prob = (turning || s_div) ? 0.0 : pm;
                         const bool take_main = u_main < prob;
                         __syncwarp(gmask);
                         if (lig == 0) {
@@ -362,7 +384,8 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
                             for (int s = 0; s < NPL; ++s) ll_main[s] = ll_sub[s];
                         }
                         m_depth += 1;
-                        m_weight = logaddexp(m_weight, s_weight);
+                        // logaddexp(m_weight, s_weight) = max + log(1 + exp(-|d|)), with exp(-|d|) from exp(d) above
+                        m_weight = isnan(dlt_m) ? -INFINITY : fmax(m_weight, s_weight) + log_pos(1.0 + (dlt_m <= 0.0 ? pm : 1.0 / pm));
                         m_div = s_div;
                         m_sum_acc += s_sum_acc;
                         m_nprop += s_nprop;
@@ -384,9 +407,9 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
                                 da_t += 1;
                                 da_gavg = (1.0 - 1.0 / (da_t + 10)) * da_gavg + (p.cfg.target_accept - accept_prob) / (da_t + 10);
                                 da_x = da_prox - sqrt((double)da_t) / 0.05 * da_gavg;
-                                const double wt = pow((double)da_t, -0.75);
+                                const double wt = exp_cold(-0.75 * log_cold((double)da_t));
                                 da_xavg = (1.0 - wt) * da_xavg + wt * da_x;
-                                eps = (t == W - 1) ? exp(da_xavg) : exp(da_x);
+                                eps = exp_cold((t == W - 1) ? da_xavg : da_x);
                                 eps = fmax(eps, 2.2250738585072014e-308);
                                 const bool is_middle = (0 < window_idx) && (window_idx < p.n_windows - 1);
                                 if (is_middle) {
@@ -445,8 +468,9 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
 #pragma unroll
                                 for (int s = 0; s < NPL; ++s) {
                                     const double v = ll_cur[s];
-                                    if (v > w_max[s]) { w_sum[s] = w_sum[s] * exp(w_max[s] - v) + 1.0; w_max[s] = v; }
-                                    else w_sum[s] += exp(v - w_max[s]);
+                                    const double ed = exp_cold(-fabs(v - w_max[s]));  // exp(-inf) = 0 on the first draw
+                                    if (v > w_max[s]) { w_sum[s] = fma(w_sum[s], ed, 1.0); w_max[s] = v; }
+                                    else w_sum[s] += ed;
                                     const double dpre = v - w_mean[s];
                                     w_mean[s] += dpre / (double)(si + 1);
                                     w_m2[s] += dpre * (v - w_mean[s]);
@@ -515,7 +539,7 @@ __global__ void __launch_bounds__(WARPS * 32) nuts_kernel(const FitLaunch p) {
         for (int s = 0; s < NPL; ++s) {
             if (ob.act[s] && !failed && S > 0) {
                 const int dense = (mask == 2 ? P : 0) + s * GW + lig;
-                const double lppd_i = logC[s] + w_max[s] + log(w_sum[s]) - log((double)S);
+                const double lppd_i = logC[s] + w_max[s] + log_cold(w_sum[s]) - log_cold((double)S);
                 const double pw_i = w_m2[s] / (double)S;
                 wout[dense] = lppd_i;
                 wout[R + dense] = pw_i;

@@ -21,7 +21,7 @@ template <int MODEL>
 struct ModelDim { static constexpr int value = MODEL == 0 ? 4 : 2; };
 
 // per-lane observations; inactive slots carry k = N = 0 (their terms are masked out of the sums,
-// and the group's spare slot is what evaluates the position-independent lgamma(phi) for free)
+// and cost nothing: R(x, 0) = 0)
 template <int NPL>
 struct LaneObs {
     double k[NPL], N[NPL], x[NPL];
@@ -56,7 +56,9 @@ __device__ __forceinline__ void log_binom_coeff(const LaneObs<NPL>& ob, double (
 // Evaluate log p(y | theta(u)) + log prior(theta(u)) [+ log |d theta / d u| if jac] and its
 // gradient w.r.t. u, for the group's chain. `ll[s]` is the per-position log-likelihood WITHOUT
 // log C(N,k). `valid` is false where the reference would produce NaN (clip(Dz,0,1) reaching 1,
-// fits.py:50) or anything is non-finite. `has_spare`: the group's last slot is inactive.
+// fits.py:50) or anything is non-finite. `has_spare`: the group's last slot is inactive (k = N = 0),
+// so its evaluations are exactly the position-independent lgamma(phi) [null: also lgamma(alpha),
+// lgamma(beta)] that every lane needs: they are broadcast instead of being computed again.
 template <int MODEL, int NPL, int GW>
 __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double (&u)[ModelDim<MODEL>::value],
                                            int jac, const Priors& pr, bool has_spare, unsigned gmask, int lig,
@@ -97,6 +99,54 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
     }
     const double phi = delta + pr.phi_min;
 
+#if MDG_EVAL_LOOP
+    // --- rolled form: one small loop body (fits the L0 instruction cache) runs the 3 (null) or 5
+    // (PMD) lgamma/digamma evaluations of a position; signs fold them into ll, ga, gb on the fly
+    double s_ll = lp_lane, s_dD = 0.0, s_dDw = 0.0, s_dDxw = 0.0, s_dphi = 0.0;
+    bool bad = false;
+    double lgphi = 0.0, dgphi = 0.0;
+    if (!has_spare) lgam_digam_u(phi, gmask, lgphi, dgphi);
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        const double w = (MODEL == 0) ? exp(ob.x[s] * log1mq) : 1.0;
+        double Dv = (MODEL == 0) ? fma(A, w, c) : q;
+        const bool ok = (Dv > 0.0) && (Dv < 1.0);
+        bad |= (!ok) && ob.act[s];
+        Dv = ok ? Dv : 0.5;
+        const double al = Dv * phi, be = (1.0 - Dv) * phi;
+        const double kk = ob.k[s], nk = ob.N[s] - ob.k[s];
+        double lls = 0.0, ga = 0.0, gb = 0.0;
+        constexpr int NE = 5;
+#pragma unroll 1
+        for (int e = 0; e < NE; ++e) {
+            // e: 0 k+al (+,+ga) | 1 N-k+be (+,+gb) | 2 N+phi (-,-ga,-gb) | 3 al (-,-ga) | 4 be (-,-gb)
+            const double xa = (e == 0) ? kk + al : (e == 1) ? nk + be : (e == 2) ? ob.N[s] + phi : (e == 3) ? al : be;
+            double l, d;
+            lgam_digam_u(xa, gmask, l, d);
+            if (MODEL == 1 && e >= 3) {
+                // null model: alpha, beta are position independent: the spare slot evaluated them at e = 0, 1
+                continue;
+            }
+            const double sg = (e < 2) ? 1.0 : -1.0;
+            lls = fma(sg, l, lls);
+            if (e == 0 || e == 2 || e == 3) ga = fma(sg, d, ga);
+            if (e == 1 || e == 2 || e == 4) gb = fma(sg, d, gb);
+            if (e == 2 && has_spare && s == NPL - 1) {
+                lgphi = __shfl_sync(gmask, l, GW - 1, GW);
+                dgphi = __shfl_sync(gmask, d, GW - 1, GW);
+            }
+        }
+        // (the rolled variant is an experiment for the PMD model with a spare slot)
+        lls += lgphi; ga += dgphi; gb += dgphi;
+        const double dD = phi * (ga - gb);
+        const double dphi = fma(Dv, ga - gb, gb);
+        ll[s] = lls;
+        if (ob.act[s]) {
+            s_ll += lls; s_dD += dD; s_dphi += dphi;
+            if (MODEL == 0) { const double dw = dD * w; s_dDw += dw; s_dDxw = fma(dw, ob.x[s], s_dDxw); }
+        }
+    }
+#else
     // --- per-position special functions -------------------------------------------------------
     double lg1[NPL], lg2[NPL], lg3[NPL], dg1[NPL], dg2[NPL], dg3[NPL];
     double lga[NPL], lgb[NPL], dga[NPL], dgb[NPL], Dz[NPL], w[NPL];
@@ -110,12 +160,12 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
         Dv = ok ? Dv : 0.5;
         Dz[s] = Dv;
         double al = Dv * phi, be = (1.0 - Dv) * phi;
-        lgam_digam(ob.k[s] + al, lg1[s], dg1[s]);
-        lgam_digam(ob.N[s] - ob.k[s] + be, lg2[s], dg2[s]);
-        lgam_digam(ob.N[s] + phi, lg3[s], dg3[s]);
+        lgam_digam_u(ob.k[s] + al, gmask, lg1[s], dg1[s]);
+        lgam_digam_u(ob.N[s] - ob.k[s] + be, gmask, lg2[s], dg2[s]);
+        lgam_digam_u(ob.N[s] + phi, gmask, lg3[s], dg3[s]);
         if (MODEL == 0) {
-            lgam_digam(al, lga[s], dga[s]);
-            lgam_digam(be, lgb[s], dgb[s]);
+            lgam_digam_u(al, gmask, lga[s], dga[s]);
+            lgam_digam_u(be, gmask, lgb[s], dgb[s]);
         }
     }
     // position-independent pieces: the spare slot (k = N = 0) has just evaluated them
@@ -124,7 +174,7 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
         lgphi = __shfl_sync(gmask, lg3[NPL - 1], GW - 1, GW);
         dgphi = __shfl_sync(gmask, dg3[NPL - 1], GW - 1, GW);
     } else {
-        lgam_digam(phi, lgphi, dgphi);
+        lgam_digam_u(phi, gmask, lgphi, dgphi);
     }
     if (MODEL == 1) {
         double ua, da_, ub, db_;
@@ -134,8 +184,8 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
             ub = __shfl_sync(gmask, lg2[NPL - 1], GW - 1, GW);
             db_ = __shfl_sync(gmask, dg2[NPL - 1], GW - 1, GW);
         } else {
-            lgam_digam(q * phi, ua, da_);
-            lgam_digam((1.0 - q) * phi, ub, db_);
+            lgam_digam_u(q * phi, gmask, ua, da_);
+            lgam_digam_u((1.0 - q) * phi, gmask, ub, db_);
         }
 #pragma unroll
         for (int s = 0; s < NPL; ++s) { lga[s] = ua; dga[s] = da_; lgb[s] = ub; dgb[s] = db_; }
@@ -163,6 +213,7 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
             }
         }
     }
+#endif
     s_ll = group_sum<GW>(s_ll, gmask);
     s_dD = group_sum<GW>(s_dD, gmask);
     s_dphi = group_sum<GW>(s_dphi, gmask);
@@ -194,15 +245,15 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
 // constrained parameters (q, A, c, phi) of an unconstrained state; null model: A = c = NaN
 template <int MODEL>
 __device__ __forceinline__ void constrain(const double (&u)[ModelDim<MODEL>::value], double phi_min, double (&th)[4]) {
-    th[0] = 1.0 / (1.0 + exp(-u[0]));
+    th[0] = sigmoid_cold(u[0]);
     if (MODEL == 0) {
-        th[1] = 1.0 / (1.0 + exp(-u[1]));
-        th[2] = 1.0 / (1.0 + exp(-u[2]));
-        th[3] = exp(u[3]) + phi_min;
+        th[1] = sigmoid_cold(u[1]);
+        th[2] = sigmoid_cold(u[2]);
+        th[3] = exp_cold(u[3]) + phi_min;
     } else {
         th[1] = nan("");
         th[2] = nan("");
-        th[3] = exp(u[1]) + phi_min;
+        th[3] = exp_cold(u[1]) + phi_min;
     }
 }
 
