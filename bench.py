@@ -123,7 +123,7 @@ def cpu_baseline(g, args, n_sample=None, threads=0):
     O.build()
     cores = threads or (os.cpu_count() or 1)
     sel = np.flatnonzero(g["passes"])
-    n_sample = n_sample or max(8, min(len(sel), 6 * cores))
+    n_sample = n_sample or max(8, min(len(sel), 64 * cores))  # ~10 s of CPU work on all cores
     # an evenly spread sample of the same TaxIDs the GPU fits
     pick = sel[np.linspace(0, len(sel) - 1, n_sample).astype(int)]
     cfg = O.default_config()
@@ -137,26 +137,42 @@ def cpu_baseline(g, args, n_sample=None, threads=0):
                       "restated reference (numpyro unavailable offline)"}, dt
 
 
+def workload_config(args, world, n_in_tax=None, n_rows=None):
+    P = args.max_position
+    shape = f" ({n_in_tax} input TaxIDs, {n_rows} rows)" if n_in_tax else ""
+    return {
+        "workload": f"cfg2: synthetic heavy-tailed mismatch matrix, {args.taxa_per_gpu} fitted TaxIDs per GPU{shape}, "
+                    f"+-{P} positions, counts + MAP + 6 NUTS runs (500 warm-up + 1000 draws) + WAIC + predictive D_max",
+        "taxa_per_gpu": args.taxa_per_gpu, "max_position": P,
+        "partition": f"by TaxID over {world} GPU(s), no collective on the fit path",
+        "l2": "flushed between steps (256 MiB write)"}
+
+
 def run_reference(args):
+    """The reference arm: the reference's algorithm on the host cores. numpyro/jax cannot be
+    installed offline, so this times the C restatement (oracle) with all host threads, each step
+    on a bounded, evenly spread sample of the same 10k-TaxID workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     g = workload(args, 0)
     cores = os.cpu_count() or 1
-    n_sample = max(8, 3 * cores)
+    n_fit = int(g["passes"].sum())
+    n_sample = max(8, min(n_fit, 32 * cores))
     for _ in range(args.warmup):
-        cpu_baseline(g, args, n_sample=max(4, cores // 2))
+        cpu_baseline(g, args, n_sample=max(4, 2 * cores))
     times, last = [], None
     for _ in range(args.steps):
         last, dt = cpu_baseline(g, args, n_sample=n_sample)
         times.append(dt)
     value = n_sample * len(times) / sum(times)
     last["value"] = value
+    cfg = workload_config(args, args.gpus, len(g["tax_ids"]), len(g["tax_id"]))
+    cfg["reference_sample_per_step"] = n_sample
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg2 sample: {n_sample} TaxIDs per step of the 10k-TaxID workload", "max_position": args.max_position},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -358,12 +374,7 @@ def main():
             "metric": METRIC, "value": dev_fits / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"cfg2: synthetic heavy-tailed mismatch matrix, {args.taxa_per_gpu} fitted TaxIDs per GPU "
-                            f"({n_in_tax} input TaxIDs, {n_rows} rows), +-{P} positions, counts + MAP + 6 NUTS runs "
-                            "(500 warm-up + 1000 draws) + WAIC + predictive D_max",
-                "taxa_per_gpu": args.taxa_per_gpu, "max_position": P, "partition": f"by TaxID over {world} GPU(s), no collective on the fit path",
-                "l2": "flushed between steps (256 MiB write)"},
+            "config": workload_config(args, world, n_in_tax, n_rows),
             "e2e": {"value": e2e_fits / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(e2e_bytes["h2d"]),
                     "d2h_bytes_per_step": int(e2e_bytes["d2h"]), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(stats["launches"]),

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 
@@ -120,6 +121,10 @@ int persistent_grid(K kernel, int threads, size_t smem, int num_sms, long long i
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (per_sm < 1) per_sm = 1;
+    if (const char* cap_env = getenv("MDG_MAX_CTAS_PER_SM")) {  // occupancy experiments
+        int c = atoi(cap_env);
+        if (c >= 1 && c < per_sm) per_sm = c;
+    }
     long long want = (items + items_per_block - 1) / items_per_block;
     long long cap = (long long)per_sm * num_sms;
     return (int)std::max<long long>(1, std::min(want, cap));
