@@ -725,6 +725,7 @@ namespace {
 
 __global__ void test_lgam_kernel(long long n, const double* x, double* lg, double* dg) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    log_table_init();
     if (i < n) {
         double a, b;
         lgam_digam(x[i], a, b);
@@ -747,6 +748,7 @@ __global__ void test_logp_kernel(int P, const uint32_t* k, const uint32_t* N, Pr
     constexpr int D = ModelDim<MODEL>::value;
     const int lane = threadIdx.x & 31;
     const long long e = blockIdx.x;
+    log_table_init();
     if (e >= n_eval) return;
     LaneObs<NPL> ob;
     load_obs<NPL, 32>(ob, k, N, P, mask, lane);

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
     const int W = p.cfg.num_warmup, S = p.cfg.num_samples, P = p.P;
     const int max_depth = p.cfg.max_tree_depth < kMaxTreeDepth ? p.cfg.max_tree_depth : kMaxTreeDepth;
     const double log_target_heur = -0.22314355131420976;  // log(0.8)
+    log_table_init();
 
     for (;;) {
         if (lane == 0) sh_item[warp] = atomicAdd(p.work_counter, 1u);
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                     if (isnan(dE)) dE = INFINITY;
                     const double leaf_w = -dE;
                     const bool leaf_div = dE > p.cfg.max_delta_energy;
-                    const double leaf_acc = fmin(1.0, exp(-dE));
+                    const double leaf_acc = fmin(1.0, exp_fast(-dE));
                     const int leaf_idx = s_nprop;
                     bool take;
                     if (leaf_idx == 0) {
@@ -307,8 +308,8 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                         uniform2(philox4x32(key, leaf_counter, (uint32_t)t, c2word(run_kind, P_SUB), 0u), us, unused);
                         // expit(d) and logaddexp share one exponential: e = exp(-|d|)
                         const double dlt = leaf_w - s_weight;
-                        const double ed = exp(-fabs(dlt));
-                        const double inv = 1.0 / (1.0 + ed);
+                        const double ed = exp_fast(-fabs(dlt));
+                        const double inv = rcp_pos(1.0 + ed);
                         const double prob = dlt >= 0.0 ? inv : ed * inv;
                         take = us < prob;  // NaN -> false
                         s_weight = isnan(dlt) ? -INFINITY : fmax(s_weight, leaf_w) + log_pos(1.0 + ed);
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                     } else {
                         // ---- subtree finished: _combine_tree(..., biased_transition=True) ----
                         const double dlt_m = s_weight - m_weight;
-                        const double pm = exp(dlt_m);
+                        const double pm = exp_fast(dlt_m);
                         const double prob = (turning || s_div) ? 0.0 : pm;
                         const bool take_main = u_main < prob;
                         __syncwarp(gmask);
@@ -756,6 +757,7 @@ template <int NPL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) map_kernel(const MapLaunch p) {
     __shared__ unsigned int sh_item[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    log_table_init();
     for (;;) {
         if (lane == 0) sh_item[warp] = atomicAdd(p.work_counter, 1u);
         __syncwarp();

@@ -71,12 +71,12 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
     double myu = u[0];
 #pragma unroll
     for (int j = 1; j < D; ++j) myu = (lig == j) ? u[j] : myu;
-    double e = exp(-fabs(myu));
-    double l1p = log1p(e);
-    double inv = 1.0 / (1.0 + e);
+    double e = exp_fast(-fabs(myu));
+    double l1p = log_pos(1.0 + e);  // absolute accuracy 1e-17 is all the log-density needs
+    double inv = rcp_pos(1.0 + e);
     double sp = fmax(myu, 0.0) + l1p;             // softplus(u)
     double sg = (myu >= 0.0) ? inv : e * inv;     // sigmoid(u)
-    double ex = (myu >= 0.0) ? 1.0 / e : e;       // exp(u)
+    double ex = exp_fast(myu);                      // exp(u)
     // this lane's prior (+ Jacobian) term of the log density
     double lp_lane = 0.0;
     {
@@ -153,7 +153,7 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
     bool bad = false;
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
-        w[s] = (MODEL == 0) ? exp(ob.x[s] * log1mq) : 1.0;
+        w[s] = (MODEL == 0) ? exp_fast(ob.x[s] * log1mq) : 1.0;
         double Dv = (MODEL == 0) ? fma(A, w[s], c) : q;
         bool ok = (Dv > 0.0) && (Dv < 1.0);
         bad |= (!ok) && ob.act[s];

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(WARPS * 32) ppc_kernel(const PpcLaunch p) {
     uint32_t* buf = sh_sort + (size_t)warp * p.s_pad;
     const int S = p.cfg.num_samples, P = p.P, n = p.s_pad;
     const unsigned total = (unsigned)p.n_tax * (unsigned)p.items_per_tax;
+    log_table_init();
     for (;;) {
         if (lane == 0) sh_item[warp] = atomicAdd(p.work_counter, 1u);
         __syncwarp();
