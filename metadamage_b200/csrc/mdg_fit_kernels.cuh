@@ -55,6 +55,26 @@ struct GroupShared {
     double rck[kMaxTreeDepth][D], rsck[kMaxTreeDepth][D];
     double wf_mean[D], wf_m2[D];
     double acc_mean[5], acc_m2[5];
+    // cold group-uniform chain state (touched once per transition / doubling, never inside the
+    // gradient evaluation). Kept here, 8 bytes per value per chain, instead of in registers: the
+    // compiler's spills would replicate each of them 32x in local memory (ncu: 866 B of spills per
+    // thread at 128 registers = 443 KB per SM, more than the L1 holds).
+    double da_x, da_xavg, da_gavg, da_prox, mean_accept, h_step, h_Er;
+    double m_weight, m_sum_acc, m_pe_p, u_main, pe_cur, eps, s_pe_p;
+    double m_rsum[D];
+    int da_t, wf_n, window_idx, h_last, h_dir, m_nprop;
+    uint32_t h_att, h_call, init_attempt, n_div;
+};
+
+// cold per-lane state of one warp: element (slot s, lane l) at [s][l] (bank-conflict free)
+template <int NPL>
+struct WarpLanes {
+    double ll_cur[NPL][32], ll_main[NPL][32], w_max[NPL][32], w_sum[NPL][32], w_mean[NPL][32], w_m2[NPL][32], logC[NPL][32];
+};
+
+struct LaneRef {  // view of one lane's column of a [NPL][32] array, indexed by slot
+    double* p;
+    __device__ __forceinline__ double& operator[](int s) const { return p[s * 32]; }
 };
 
 enum Phase : int { PH_INIT = 0, PH_HEUR = 1, PH_LEAF = 2 };
@@ -112,13 +132,14 @@ __device__ __forceinline__ void draw_momentum(uint2 key, uint32_t c1, uint32_t c
 // K4: NUTS. MODEL 0 = PMD, 1 = null. NPL positions per lane. GW lanes per chain.
 // ---------------------------------------------------------------------------------------------
 #ifndef MDG_NUTS_MINBLOCKS
-#define MDG_NUTS_MINBLOCKS 3
+#define MDG_NUTS_MINBLOCKS 4
 #endif
 template <int MODEL, int NPL, int GW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(const FitLaunch p) {
     constexpr int D = ModelDim<MODEL>::value;
     constexpr int GROUPS = 32 / GW;
     __shared__ GroupShared<D> sh_all[WARPS * GROUPS];
+    __shared__ WarpLanes<NPL> sh_lanes[WARPS];
     __shared__ unsigned int sh_item[WARPS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,44 +166,56 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
 
         LaneObs<NPL> ob;
         load_obs<NPL, GW>(ob, p.k + (size_t)tax * 2 * P, p.N + (size_t)tax * 2 * P, P, mask, lig);
-        double logC[NPL];
-        log_binom_coeff<NPL>(ob, logC);
+        WarpLanes<NPL>& wl = sh_lanes[warp];
+        const LaneRef logC{&wl.logC[0][lane]}, ll_cur{&wl.ll_cur[0][lane]}, ll_main{&wl.ll_main[0][lane]};
+        const LaneRef w_max{&wl.w_max[0][lane]}, w_sum{&wl.w_sum[0][lane]}, w_mean{&wl.w_mean[0][lane]}, w_m2{&wl.w_m2[0][lane]};
+        {
+            double lc[NPL];
+            log_binom_coeff<NPL>(ob, lc);
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) {
+                logC[s] = lc[s];
+                w_max[s] = -INFINITY; w_sum[s] = 0.0; w_mean[s] = 0.0; w_m2[s] = 0.0; ll_cur[s] = 0.0; ll_main[s] = 0.0;
+            }
+        }
 
-        // ---- chain registers (group-uniform unless noted) ----
+        // ---- hot chain state in registers (group-uniform unless noted) ----
         double imm[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) imm[j] = 1.0;
-        double eps = p.cfg.init_step_size;
-        double pe_cur = 0.0;
-        double ll_cur[NPL], ll_main[NPL], ll_sub[NPL];  // per lane
-        // WAIC accumulators (per lane): online logsumexp and Welford over the kept draws
-        double w_max[NPL], w_sum[NPL], w_mean[NPL], w_m2[NPL];
+        double ll_sub[NPL];  // per lane
 #pragma unroll
-        for (int s = 0; s < NPL; ++s) { w_max[s] = -INFINITY; w_sum[s] = 0.0; w_mean[s] = 0.0; w_m2[s] = 0.0; ll_cur[s] = ll_main[s] = ll_sub[s] = 0.0; }
-        // dual averaging
-        double da_x = 0.0, da_xavg = 0.0, da_gavg = 0.0, da_prox = 0.0;
-        int da_t = 0, wf_n = 0, window_idx = 0;
-        double mean_accept = 0.0;
-        uint32_t n_grad = 0, n_div = 0;
+        for (int s = 0; s < NPL; ++s) ll_sub[s] = 0.0;
+        uint32_t n_grad = 0;
         int failed = 0;
-        // tree registers
-        double E0 = 0.0, m_weight = 0.0, m_sum_acc = 0.0, m_pe_p = 0.0, u_main = 0.0;
-        double m_rsum[D], s_rsum[D];
-        int m_nprop = 0, m_depth = 0;
+        double E0 = 0.0;
+        double s_rsum[D];
+        int m_depth = 0;
         bool m_turning = false, m_div = false, going_right = true;
-        double s_weight = 0.0, s_sum_acc = 0.0, s_pe_p = 0.0;
+        double s_weight = 0.0, s_sum_acc = 0.0;
         int s_nprop = 0;
         bool s_div = false;
         uint32_t leaf_counter = 0;
-        // heuristic registers
-        double h_step = 0.0, h_Er = 0.0;
-        int h_last = 0, h_dir = 0;
-        uint32_t h_att = 0, h_call = 0;
         // leapfrog source
         double zf[D], rf[D], gf[D], e = 0.0;
         int phase = PH_INIT;
-        uint32_t init_attempt = 0;
         int t = 0;
+        // ---- cold chain state: references into shared memory (every lane of the group writes
+        // the same value, reads are broadcasts) ----
+        double& eps = sh.eps; double& pe_cur = sh.pe_cur;
+        double& da_x = sh.da_x; double& da_xavg = sh.da_xavg; double& da_gavg = sh.da_gavg; double& da_prox = sh.da_prox;
+        int& da_t = sh.da_t; int& wf_n = sh.wf_n; int& window_idx = sh.window_idx;
+        double& mean_accept = sh.mean_accept; uint32_t& n_div = sh.n_div;
+        double& m_weight = sh.m_weight; double& m_sum_acc = sh.m_sum_acc; double& m_pe_p = sh.m_pe_p; double& u_main = sh.u_main;
+        double (&m_rsum)[D] = sh.m_rsum; int& m_nprop = sh.m_nprop; double& s_pe_p = sh.s_pe_p;
+        double& h_step = sh.h_step; double& h_Er = sh.h_Er; int& h_last = sh.h_last; int& h_dir = sh.h_dir;
+        uint32_t& h_att = sh.h_att; uint32_t& h_call = sh.h_call; uint32_t& init_attempt = sh.init_attempt;
+        __syncwarp(gmask);
+        eps = p.cfg.init_step_size; pe_cur = 0.0;
+        da_x = 0.0; da_xavg = 0.0; da_gavg = 0.0; da_prox = 0.0; da_t = 0; wf_n = 0; window_idx = 0;
+        mean_accept = 0.0; n_div = 0u;
+        m_weight = 0.0; m_sum_acc = 0.0; m_pe_p = 0.0; u_main = 0.0; m_nprop = 0; s_pe_p = 0.0;
+        h_step = 0.0; h_Er = 0.0; h_last = 0; h_dir = 0; h_att = 0u; h_call = 0u; init_attempt = 0u;
         if (lig == 0) {
 #pragma unroll
             for (int j = 0; j < D; ++j) { sh.wf_mean[j] = 0.0; sh.wf_m2[j] = 0.0; }
