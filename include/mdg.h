@@ -251,6 +251,9 @@ int mdg_test_logp_grad(mdg_ctx* ctx, int max_position, const uint32_t* k, const 
                        int64_t n_eval, const double* u,
                        double* out_logp, double* out_grad, double* out_ll);
 
+/* the fit kernels' own table-driven exp and log at x[0..n) (log only where x > 0); host pointers */
+int mdg_test_exp_log(mdg_ctx* ctx, int64_t n, const double* x, double* out_exp, double* out_log);
+
 /* Philox4x32-10 block for (key, counter), 4 words out; n blocks; host pointers */
 int mdg_test_philox(mdg_ctx* ctx, int64_t n, const uint32_t* key2, const uint32_t* ctr4,
                     uint32_t* out4);

@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
     "mdg_fit_batch",
     "mdg_test_lgamma_digamma",
     "mdg_test_logp_grad",
+    "mdg_test_exp_log",
     "mdg_test_philox",
     "mdg_measure_fp64_peak",
 )
@@ -67,6 +68,7 @@ def load():
     )
     lib.mdg_fit_batch.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, C.POINTER(FitConfig)] + [vp] * 7
     lib.mdg_test_lgamma_digamma.argtypes = [vp, i64, vp, vp, vp]
+    lib.mdg_test_exp_log.argtypes = [vp, i64, vp, vp, vp]
     lib.mdg_test_logp_grad.argtypes = [vp, i32, vp, vp, C.POINTER(FitConfig), i32, i32, i32, i64, vp, vp, vp, vp]
     lib.mdg_test_philox.argtypes = [vp, i64, vp, vp, vp]
     lib.mdg_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]

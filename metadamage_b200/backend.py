@@ -185,6 +185,13 @@ class Context:
         _lib.check(self._lib.mdg_test_lgamma_digamma(self._h, x.size, ptr(x), ptr(lg), ptr(dg)))
         return lg, dg
 
+    def exp_log(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        ex = np.empty_like(x)
+        lg = np.empty_like(x)
+        _lib.check(self._lib.mdg_test_exp_log(self._h, x.size, ptr(x), ptr(ex), ptr(lg)))
+        return ex, lg
+
     def philox(self, key2, ctr4):
         key2 = np.ascontiguousarray(key2, dtype=np.uint32).reshape(-1, 2)
         ctr4 = np.ascontiguousarray(ctr4, dtype=np.uint32).reshape(-1, 4)

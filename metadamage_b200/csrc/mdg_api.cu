@@ -409,6 +409,7 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
     for (int step = 0; step < 3; ++step) {
         cl.T = ladder_T[step];
         cl.L = ladder_L[step];
+        if (step == 0) if (const char* t_env = getenv("MDG_COUNTS_T")) { int tv = atoi(t_env); if (tv >= 64 && tv % 16 == 0) cl.T = tv; }  // tile-size experiments
         // shrink the tile (never the lookahead) until it fits the 227 KB of shared memory
         while (cl.T > 16 && fixed_bytes + row_bytes * (size_t)(cl.T + cl.L) > 227 * 1024 - 1024) cl.T -= 16;
         const int cap = cl.T + cl.L;
@@ -734,6 +735,15 @@ __global__ void test_lgam_kernel(long long n, const double* x, double* lg, doubl
     }
 }
 
+__global__ void test_exp_log_kernel(long long n, const double* x, double* ex, double* lg) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    log_table_init();
+    if (i < n) {
+        ex[i] = exp_fast(x[i]);
+        lg[i] = x[i] > 0.0 ? log_pos(x[i]) : nan("");
+    }
+}
+
 __global__ void test_philox_kernel(long long n, const uint32_t* key2, const uint32_t* ctr4, uint32_t* out4) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) {
@@ -801,6 +811,22 @@ int mdg_test_lgamma_digamma(mdg_ctx* ctx, int64_t n, const double* x, double* ou
     MDG_CUDA_TRY(cudaGetLastError());
     MDG_CUDA_TRY(cudaMemcpyAsync(out_lgamma, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MDG_CUDA_TRY(cudaMemcpyAsync(out_digamma, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MDG_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return MDG_OK;
+}
+
+int mdg_test_exp_log(mdg_ctx* ctx, int64_t n, const double* x, double* out_exp, double* out_log) {
+    if (!ctx || n < 0) { set_error("invalid argument"); return MDG_ERR_INVALID; }
+    if (n == 0) return MDG_OK;
+    DeviceGuard guard(ctx->device);
+    int rc = ctx->buf[20].ensure((size_t)n * 24);
+    if (rc) return rc;
+    double* d = ctx->buf[20].as<double>();
+    MDG_CUDA_TRY(cudaMemcpyAsync(d, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    test_exp_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, d, d + n, d + 2 * n);
+    MDG_CUDA_TRY(cudaGetLastError());
+    MDG_CUDA_TRY(cudaMemcpyAsync(out_exp, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MDG_CUDA_TRY(cudaMemcpyAsync(out_log, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MDG_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return MDG_OK;
 }

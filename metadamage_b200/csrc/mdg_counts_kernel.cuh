@@ -16,7 +16,8 @@
 //     loads and writes the row-local outputs (reference sums, error rates, z) of the tile's
 //     nominal rows straight from registers with 128-bit stores (tile starts are 16-byte aligned
 //     for every column type); y_sum_total and the cut flag follow once the TaxID sums are known;
-//   * per-TaxID sums are a short serial loop of one thread per TaxID over staged values; the
+//   * per-TaxID sums are a short serial loop of one thread per TaxID over staged values (a warp
+//     per TaxID with a shuffle reduction was measured 7 % slower); the
 //     dense k/N (and the optional noise) of KEPT TaxIDs use one warp per TaxID, lane = row.
 // The first version (one warp per TaxID for everything) was instruction-issue bound at 30 warp
 // instructions per row (profiles/r01_counts_ncu.md); this layout needs a few.
@@ -87,14 +88,25 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     return v;
 }
 
-// float32(double(k) / double(n)) with 0/0 -> 0 (counts.py:99, 254). Operands are forced into
-// the normal range so that the FP64 division never leaves its fast path.
+// float32(double(k) / double(n)) with 0/0 -> 0 (counts.py:99, 254), bit-exact.
+// Fast path: q = k * (1/n) refined once (Markstein): at most 1 ulp(double) from the correctly
+// rounded quotient, which changes the float32 result only if q sits within a few ulps of a
+// float32 rounding boundary; exactly those (about 1 in 2^26) values take the IEEE division.
 __device__ __forceinline__ float error_rate(uint32_t k, uint32_t n) {
-    const double q = (double)(k ? k : 1u) / (double)(n ? n : 1u);
+    const double a = (double)(k ? k : 1u), b = (double)(n ? n : 1u);
+    const double y = rcp_pos(b);
+    const double q0 = a * y;
+    double q = fma(fma(-b, q0, a), y, q0);
+    const unsigned low = (unsigned)__double2loint(q) & 0x1fffffffu;  // the 29 bits float32 drops
+    if (low - 0x0ffffffcu <= 8u) q = a / b;                          // within 4 ulps of a tie: exact path
     return (k && n) ? (float)q : 0.0f;
 }
 
-__global__ void __launch_bounds__(kCountsThreads) counts_reduce_kernel(const CountsLaunch p) {
+#ifndef MDG_COUNTS_MINBLOCKS
+#define MDG_COUNTS_MINBLOCKS 6
+#endif
+
+__global__ void __launch_bounds__(kCountsThreads, MDG_COUNTS_MINBLOCKS) counts_reduce_kernel(const CountsLaunch p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cap = p.T + p.L;  // rows staged per tile (multiple of 16)
     // ---- shared layout (every array starts 16-byte aligned because cap % 16 == 0) ----
