@@ -6,20 +6,12 @@
 #include <math.h>
 #include "mdg.h"
 
-// A/B switches of the kernel tuning experiments (profiles/r01_nuts_tuning.md). Defaults = shipped.
-// Measured on B200, 10k TaxIDs, NUTS kernels only: LOGFN 1 -10 %, UNIFORM_SHIFT 1 +50 %,
-// COLD_INLINE 0 +3 %, EVAL_LOOP 1 +20 %.
+// Kernel tuning switches kept for A/B measurements (profiles/r01_nuts_tuning.md). Defaults = shipped.
 #ifndef MDG_LOGFN
-#define MDG_LOGFN 1          // 1: log_pos (constant-bank coefficients); 0: CUDA log()
+#define MDG_LOGFN 1          // 1: table-driven log_pos; 0: CUDA log()
 #endif
 #ifndef MDG_COLD_INLINE
 #define MDG_COLD_INLINE 1    // 1: everything inlined; 0: cold helpers (Philox, Box-Muller, logaddexp, ...) out of line
-#endif
-#ifndef MDG_UNIFORM_SHIFT
-#define MDG_UNIFORM_SHIFT 0  // 0: small-argument shift under a per-lane branch; 1: under a group-uniform branch
-#endif
-#ifndef MDG_EVAL_LOOP
-#define MDG_EVAL_LOOP 0      // 1: the five lgamma/digamma evaluations as a rolled loop (small I-cache footprint)
 #endif
 #if MDG_COLD_INLINE
 #define MDG_COLD __forceinline__
@@ -253,21 +245,6 @@ __device__ __forceinline__ void stirling(double y, double t, double& st, double&
 __device__ __forceinline__ void lgam_digam_u(double x, unsigned gmask, double& lg, double& dg) {
     double y = x, logP = 0.0, dP = 0.0;
     const bool small = x < 10.0;
-#if MDG_UNIFORM_SHIFT
-    if (__any_sync(gmask, small)) {
-        double P = small ? x : 1.0, Q = small ? 1.0 : 0.0;
-#pragma unroll
-        for (int i = 1; i < 10; ++i) {
-            const double xi = small ? x + (double)i : 1.0;
-            Q = fma(Q, xi, small ? P : 0.0);
-            P *= xi;
-        }
-        logP = log_sel(P);
-        dP = Q / P;
-        y = small ? x + 10.0 : x;
-    }
-    const double t = rcp_pos(y);
-#else
     double t;
     if (small) {
         double P = x, Q = 1.0;
@@ -285,7 +262,6 @@ __device__ __forceinline__ void lgam_digam_u(double x, unsigned gmask, double& l
     } else {
         t = rcp_pos(y);
     }
-#endif
     double st, d;
     stirling(y, t, st, d);
     lg = (st + 0.91893853320467274178) - logP;

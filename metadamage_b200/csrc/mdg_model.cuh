@@ -99,54 +99,6 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
     }
     const double phi = delta + pr.phi_min;
 
-#if MDG_EVAL_LOOP
-    // --- rolled form: one small loop body (fits the L0 instruction cache) runs the 3 (null) or 5
-    // (PMD) lgamma/digamma evaluations of a position; signs fold them into ll, ga, gb on the fly
-    double s_ll = lp_lane, s_dD = 0.0, s_dDw = 0.0, s_dDxw = 0.0, s_dphi = 0.0;
-    bool bad = false;
-    double lgphi = 0.0, dgphi = 0.0;
-    if (!has_spare) lgam_digam_u(phi, gmask, lgphi, dgphi);
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) {
-        const double w = (MODEL == 0) ? exp(ob.x[s] * log1mq) : 1.0;
-        double Dv = (MODEL == 0) ? fma(A, w, c) : q;
-        const bool ok = (Dv > 0.0) && (Dv < 1.0);
-        bad |= (!ok) && ob.act[s];
-        Dv = ok ? Dv : 0.5;
-        const double al = Dv * phi, be = (1.0 - Dv) * phi;
-        const double kk = ob.k[s], nk = ob.N[s] - ob.k[s];
-        double lls = 0.0, ga = 0.0, gb = 0.0;
-        constexpr int NE = 5;
-#pragma unroll 1
-        for (int e = 0; e < NE; ++e) {
-            // e: 0 k+al (+,+ga) | 1 N-k+be (+,+gb) | 2 N+phi (-,-ga,-gb) | 3 al (-,-ga) | 4 be (-,-gb)
-            const double xa = (e == 0) ? kk + al : (e == 1) ? nk + be : (e == 2) ? ob.N[s] + phi : (e == 3) ? al : be;
-            double l, d;
-            lgam_digam_u(xa, gmask, l, d);
-            if (MODEL == 1 && e >= 3) {
-                // null model: alpha, beta are position independent: the spare slot evaluated them at e = 0, 1
-                continue;
-            }
-            const double sg = (e < 2) ? 1.0 : -1.0;
-            lls = fma(sg, l, lls);
-            if (e == 0 || e == 2 || e == 3) ga = fma(sg, d, ga);
-            if (e == 1 || e == 2 || e == 4) gb = fma(sg, d, gb);
-            if (e == 2 && has_spare && s == NPL - 1) {
-                lgphi = __shfl_sync(gmask, l, GW - 1, GW);
-                dgphi = __shfl_sync(gmask, d, GW - 1, GW);
-            }
-        }
-        // (the rolled variant is an experiment for the PMD model with a spare slot)
-        lls += lgphi; ga += dgphi; gb += dgphi;
-        const double dD = phi * (ga - gb);
-        const double dphi = fma(Dv, ga - gb, gb);
-        ll[s] = lls;
-        if (ob.act[s]) {
-            s_ll += lls; s_dD += dD; s_dphi += dphi;
-            if (MODEL == 0) { const double dw = dD * w; s_dDw += dw; s_dDxw = fma(dw, ob.x[s], s_dDxw); }
-        }
-    }
-#else
     // --- per-position special functions -------------------------------------------------------
     double lg1[NPL], lg2[NPL], lg3[NPL], dg1[NPL], dg2[NPL], dg3[NPL];
     double lga[NPL], lgb[NPL], dga[NPL], dgb[NPL], Dz[NPL], w[NPL];
@@ -213,7 +165,6 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
             }
         }
     }
-#endif
     s_ll = group_sum<GW>(s_ll, gmask);
     s_dD = group_sum<GW>(s_dD, gmask);
     s_dphi = group_sum<GW>(s_dphi, gmask);
