@@ -153,7 +153,7 @@ typedef struct mdg_fit_result {
 
 /* device timings of the last call on a ctx, measured with CUDA events on the ctx stream */
 typedef struct mdg_timings {
-    float counts_ms;      /* counts_reduce kernel (K1) */
+    float counts_ms;      /* counts_reduce kernel (K1); for mdg_tsv_parse: the parse kernels (K0) */
     float map_ms;         /* MAP kernel (K3) */
     float nuts_ms;        /* all NUTS kernels (K4), summed over chunks */
     float ppc_ms;         /* posterior predictive + sort + HPDI (K6) */
@@ -234,6 +234,24 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
                   mdg_fit_result* out,
                   float* out_median, float* out_hpdi_lo, float* out_hpdi_hi,
                   double* out_samples, double* out_trace, double* out_waic);
+
+/*
+ * K0 — tsv_parse: the step before the hot path. Tokenises a mismatch-matrix
+ * text file held in host memory into the SoA columns mdg_counts_reduce takes; replaces the
+ * parsing half of dd.read_csv(..., sep="\t", header=None, names=columns) (counts.py:229-235).
+ * Layouts: 22 tab-separated columns (counts.py:37-45: tax_id, tax_name, tax_rank, N_alignments,
+ * strand, position, AA..TT) or the legacy 20 columns without tax_name / tax_rank that the shipped
+ * data/input files use; a first line that does not start with a digit or '-' is a header and is
+ * skipped. `mem` says where the OUTPUT columns live (the text is always a host pointer).
+ * counts16 is [16][counts_stride]. name_span / rank_span (22-column layout, optional) receive
+ * (byte offset, length) pairs into `text` so that the host can build the two string columns.
+ * Errors: malformed line / number / value out of range -> MDG_ERR_INVALID with the line number
+ * in the message; more data lines than `capacity` -> MDG_ERR_INVALID.
+ */
+int mdg_tsv_parse(mdg_ctx* ctx, int mem, const char* text, int64_t n_bytes, int64_t capacity,
+                  int64_t* tax_id, uint32_t* n_alignments, uint8_t* is_reverse, uint8_t* pos0,
+                  uint32_t* counts16, int64_t counts_stride, int64_t* name_span, int64_t* rank_span,
+                  int64_t* out_n_rows /* host */, int32_t* out_n_cols /* host: 20 or 22 */);
 
 /* building blocks exported for the parity tests (device evaluation of single functions) */
 

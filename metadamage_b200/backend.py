@@ -74,6 +74,27 @@ class Context:
         _lib.check(self._lib.mdg_measure_fp64_peak(self._h, C.byref(out)))
         return out.value
 
+    # ------------------------------------------------------------------ K0
+    def tsv_parse(self, text, want_spans=False):
+        """Tokenise a mismatch-matrix file (bytes) on the GPU -> SoA numpy columns (counts.py:229-235)."""
+        if not isinstance(text, (bytes, bytearray, memoryview)):
+            raise TypeError("text must be bytes")
+        text = bytes(text)
+        cap = text.count(b"\n") + 1
+        out = dict(tax_id=np.empty(cap, np.int64), n_alignments=np.empty(cap, np.uint32), is_reverse=np.empty(cap, np.uint8),
+                   pos0=np.empty(cap, np.uint8), counts16=np.empty((16, cap), np.uint32),
+                   name_span=np.empty((cap, 2), np.int64) if want_spans else None,
+                   rank_span=np.empty((cap, 2), np.int64) if want_spans else None)
+        n_rows, n_cols = C.c_int64(0), C.c_int32(0)
+        _lib.check(self._lib.mdg_tsv_parse(self._h, MDG_HOST, text, len(text), cap, ptr(out["tax_id"]), ptr(out["n_alignments"]),
+                                           ptr(out["is_reverse"]), ptr(out["pos0"]), ptr(out["counts16"]), cap,
+                                           ptr(out["name_span"]), ptr(out["rank_span"]), C.byref(n_rows), C.byref(n_cols)))
+        n = n_rows.value
+        res = {k: (v[:n] if v is not None and k != "counts16" else v) for k, v in out.items()}
+        res["counts16"] = np.ascontiguousarray(out["counts16"][:, :n])
+        res["n_rows"], res["n_cols"] = n, n_cols.value
+        return res
+
     # ------------------------------------------------------------------ K1
     def counts_reduce(self, tax_id, n_alignments, is_reverse, pos0, counts16, fwd="CT", rev="GA",
                       max_position=15, min_alignments=10, min_y_sum=10, want_noise=False, want_rows=True):

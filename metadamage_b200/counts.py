@@ -82,11 +82,47 @@ def reference_row_order(n_alignments, tax_id, z):
     return np.lexsort((-order, -tax_id.astype(np.int64), -n_alignments.astype(np.int64)))
 
 
+def read_mismatch_table_gpu(filename, ctx):
+    """Same table as `read_mismatch_table`, with the numeric columns tokenised on the GPU
+    (mdg_tsv_parse, K0) instead of by pandas; the two string columns of the 22-column layout are
+    cut out of the file bytes through the (offset, length) spans the kernel returns."""
+    with open(filename, "rb") as fh:
+        text = fh.read()
+    r = ctx.tsv_parse(text, want_spans=True)
+    logger.info("tsv: %d bytes -> %d rows (parse kernels %.3f ms)", len(text), r["n_rows"], ctx.timings()["counts_ms"])
+    data = {"tax_id": r["tax_id"]}
+    if r["n_cols"] == 22:
+        for col, key in (("tax_name", "name_span"), ("tax_rank", "rank_span")):
+            spans = r[key]
+            # few distinct strings, many rows: decode each distinct (offset-independent) value once
+            uniq, inv = np.unique(spans[:, 1], return_inverse=True) if len(spans) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+            vals = np.empty(len(spans), dtype=object)
+            cache = {}
+            for i in range(len(spans)):
+                o, n = int(spans[i, 0]), int(spans[i, 1])
+                b = text[o:o + n]
+                v = cache.get(b)
+                if v is None:
+                    v = cache[b] = b.decode("utf-8", "replace")
+                vals[i] = v
+            data[col] = vals
+    else:
+        data["tax_name"] = ""
+        data["tax_rank"] = ""
+    data["N_alignments"] = r["n_alignments"]
+    data["strand"] = np.where(r["is_reverse"] == 1, "3'", "5'") if r["n_cols"] else np.zeros(0, dtype=object)
+    data["position"] = r["pos0"].astype(np.int64)
+    df = pd.DataFrame(data, columns=COLUMNS[:6])
+    for i, name in enumerate(REF_OBS_BASES):
+        df[name] = r["counts16"][i]
+    return df
+
+
 def compute_counts(cfg, df_in=None, ctx=None):
     """The GPU replacement of compute_counts_with_dask (counts.py:212-273)."""
     ctx = ctx or get_context(0)
     if df_in is None:
-        df_in = read_mismatch_table(cfg.filename)
+        df_in = read_mismatch_table_gpu(cfg.filename, ctx)
     df_in = group_rows_by_tax_id(df_in)
     fwd, rev = cfg.substitution_bases_forward, cfg.substitution_bases_reverse
     cols = soa_columns(df_in)

@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "mdg_counts_kernel.cuh"
+#include "mdg_tsv_kernel.cuh"
 #include "mdg_post_kernels.cuh"
 
 namespace mdg {
@@ -490,6 +491,130 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
     MDG_CUDA_TRY(cudaStreamSynchronize(st));
     ctx->timings.counts_ms = elapsed(ctx->ev[1], ctx->ev[2]);
     ctx->timings.total_ms = elapsed(ctx->ev[0], ctx->ev[3]);
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0
+// ---------------------------------------------------------------------------------------------
+int mdg_tsv_parse(mdg_ctx* ctx, int mem, const char* text, int64_t n_bytes, int64_t capacity, int64_t* tax_id,
+                  uint32_t* n_alignments, uint8_t* is_reverse, uint8_t* pos0, uint32_t* counts16, int64_t counts_stride,
+                  int64_t* name_span, int64_t* rank_span, int64_t* out_n_rows, int32_t* out_n_cols) {
+    if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
+    if (n_bytes < 0 || capacity < 0 || !out_n_rows || (mem != MDG_HOST && mem != MDG_DEVICE) || counts_stride < capacity ||
+        (n_bytes > 0 && !text) || (capacity > 0 && (!tax_id || !n_alignments || !is_reverse || !pos0 || !counts16))) {
+        set_error("mdg_tsv_parse: invalid argument");
+        return MDG_ERR_INVALID;
+    }
+    *out_n_rows = 0;
+    if (out_n_cols) *out_n_cols = 0;
+    ctx->timings = mdg_timings{};
+    // header detection and layout from the first line (host)
+    int64_t first = 0;
+    {
+        int64_t e = 0;
+        while (e < n_bytes && text[e] != '\n') ++e;
+        const bool header = n_bytes > 0 && !((text[0] >= '0' && text[0] <= '9') || text[0] == '-');
+        if (header) first = e < n_bytes ? e + 1 : n_bytes;
+    }
+    int64_t e1 = first;
+    int tabs = 0;
+    while (e1 < n_bytes && text[e1] != '\n') { tabs += text[e1] == '\t'; ++e1; }
+    if (first >= n_bytes) return MDG_OK;  // no data lines
+    const int n_cols = tabs + 1;
+    if (n_cols != 20 && n_cols != 22) {
+        set_error("mdg_tsv_parse: expected 20 or 22 tab-separated columns, got %d", n_cols);
+        return MDG_ERR_INVALID;
+    }
+    if (out_n_cols) *out_n_cols = n_cols;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = ctx->stream;
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+    const bool host = (mem == MDG_HOST);
+    const size_t cap = (size_t)capacity;
+    TsvLaunch tl = {};
+    tl.n_bytes = n_bytes; tl.first = first; tl.n_cols = n_cols; tl.capacity = capacity;
+    tl.n_blocks = (n_bytes - first + kTsvBlockBytes - 1) / kTsvBlockBytes;
+    int rc;
+    if ((rc = ctx->buf[22].ensure((size_t)n_bytes + 16))) return rc;
+    MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[22].ptr, text, (size_t)n_bytes, cudaMemcpyHostToDevice, st));
+    tl.text = ctx->buf[22].as<char>();
+    if ((rc = ctx->buf[23].ensure((size_t)tl.n_blocks * 12 + (cap + 2) * 8 + 256))) return rc;
+    tl.block_base = ctx->buf[23].as<long long>();
+    tl.line_start = tl.block_base + tl.n_blocks;
+    tl.block_cnt = reinterpret_cast<int*>(tl.line_start + cap + 2);
+    if ((rc = ctx->buf[2].ensure(64))) return rc;
+    long long* d_scal = ctx->buf[2].as<long long>();  // [0] newline total, [1] error flag (int), [2] error line
+    tl.n_lines = d_scal; tl.error_flag = reinterpret_cast<int*>(d_scal + 1); tl.error_line = d_scal + 2;
+    MDG_CUDA_TRY(cudaMemsetAsync(d_scal, 0, 64, st));
+    struct OutCopy { void* host_ptr; const void* dev_ptr; size_t bytes_per_row; };
+    std::vector<OutCopy> copies;
+    if (host) {
+        const size_t stride_dev = (cap + 63) & ~(size_t)63;
+        if ((rc = ctx->buf[1].ensure(cap * (8 + 4 + 1 + 1 + 32) + 16 * stride_dev * 4 + 4096))) return rc;
+        unsigned char* ob = ctx->buf[1].as<unsigned char>();
+        size_t oo = 0;
+        auto take = [&](void* hp, size_t elem) -> void* {
+            void* d = ob + oo;
+            oo += (elem * cap + 255) & ~(size_t)255;
+            if (hp) copies.push_back({hp, d, elem});
+            return d;
+        };
+        tl.tax_id = (long long*)take(tax_id, 8);
+        tl.n_align = (uint32_t*)take(n_alignments, 4);
+        tl.is_rev = (uint8_t*)take(is_reverse, 1);
+        tl.pos0 = (uint8_t*)take(pos0, 1);
+        tl.name_span = name_span ? (long long*)take(name_span, 16) : nullptr;
+        tl.rank_span = rank_span ? (long long*)take(rank_span, 16) : nullptr;
+        tl.counts16 = reinterpret_cast<uint32_t*>(ob + oo);
+        tl.stride = (long long)stride_dev;
+    } else {
+        tl.tax_id = (long long*)tax_id; tl.n_align = n_alignments; tl.is_rev = is_reverse; tl.pos0 = pos0;
+        tl.counts16 = counts16; tl.stride = counts_stride;
+        tl.name_span = (long long*)name_span; tl.rank_span = (long long*)rank_span;
+    }
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+    tsv_count_kernel<<<(unsigned)tl.n_blocks, kTsvThreads, 0, st>>>(tl);
+    MDG_CUDA_TRY(cudaGetLastError());
+    counts_scan_kernel<<<1, 1024, 0, st>>>(tl.block_cnt, tl.n_blocks, tl.block_base, tl.n_lines);
+    MDG_CUDA_TRY(cudaGetLastError());
+    long long newlines = 0;
+    MDG_CUDA_TRY(cudaMemcpyAsync(&newlines, tl.n_lines, 8, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    const long long n_lines = newlines + (text[n_bytes - 1] != '\n' ? 1 : 0);
+    if (n_lines > capacity) {
+        set_error("mdg_tsv_parse: %lld data lines but room for %lld rows", n_lines, (long long)capacity);
+        return MDG_ERR_INVALID;
+    }
+    tsv_lines_kernel<<<(unsigned)tl.n_blocks, kTsvThreads, 0, st>>>(tl);
+    MDG_CUDA_TRY(cudaGetLastError());
+    if (n_lines > 0) {
+        tsv_parse_kernel<<<(unsigned)((n_lines + kTsvThreads - 1) / kTsvThreads), kTsvThreads, 0, st>>>(tl, n_lines);
+        MDG_CUDA_TRY(cudaGetLastError());
+    }
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+    ctx->timings.n_launches = 4;
+    int h_err[2] = {0, 0};
+    long long h_line = 0;
+    MDG_CUDA_TRY(cudaMemcpyAsync(h_err, tl.error_flag, 4, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaMemcpyAsync(&h_line, tl.error_line, 8, cudaMemcpyDeviceToHost, st));
+    if (host && n_lines > 0) {
+        for (const auto& c : copies)
+            MDG_CUDA_TRY(cudaMemcpyAsync(c.host_ptr, c.dev_ptr, c.bytes_per_row * (size_t)n_lines, cudaMemcpyDeviceToHost, st));
+        for (int c = 0; c < 16; ++c)
+            MDG_CUDA_TRY(cudaMemcpyAsync(counts16 + (size_t)c * counts_stride, tl.counts16 + (size_t)c * tl.stride,
+                                         (size_t)n_lines * 4, cudaMemcpyDeviceToHost, st));
+    }
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+    MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->timings.counts_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+    ctx->timings.total_ms = elapsed(ctx->ev[0], ctx->ev[3]);
+    if (h_err[0] != TE_NONE) {
+        static const char* what[] = {"", "wrong number of fields", "malformed number", "value out of range", ""};
+        set_error("mdg_tsv_parse: %s in data line %lld", what[h_err[0] & 3], h_line + 1);
+        return MDG_ERR_INVALID;
+    }
+    *out_n_rows = n_lines;
     return MDG_OK;
 }
 

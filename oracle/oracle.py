@@ -80,6 +80,25 @@ def digamma(x):
     return np.array([lib().orc_digamma(float(v)) for v in np.atleast_1d(x)])
 
 
+def tsv_parse(text):
+    """Restatement of the tokenising half of dd.read_csv (counts.py:229-235) on bytes."""
+    text = bytes(text)
+    cap = text.count(b"\n") + 1
+    out = dict(tax_id=np.zeros(cap, np.int64), n_alignments=np.zeros(cap, np.uint32), is_reverse=np.zeros(cap, np.uint8),
+               pos0=np.zeros(cap, np.uint8), counts16=np.zeros((16, cap), np.uint32))
+    n_rows, n_cols = C.c_int64(0), C.c_int32(0)
+    rc = lib().orc_tsv_parse(text, C.c_int64(len(text)), C.c_int64(cap), ptr(out["tax_id"]), ptr(out["n_alignments"]),
+                             ptr(out["is_reverse"]), ptr(out["pos0"]), ptr(out["counts16"]), C.c_int64(cap),
+                             C.byref(n_rows), C.byref(n_cols))
+    if rc != 0:
+        raise RuntimeError(f"orc_tsv_parse failed with {rc}")
+    n = n_rows.value
+    res = {k: v[:n] for k, v in out.items() if k != "counts16"}
+    res["counts16"] = np.ascontiguousarray(out["counts16"][:, :n])
+    res["n_rows"], res["n_cols"] = n, n_cols.value
+    return res
+
+
 def counts_reduce(tax_id, n_alignments, is_reverse, pos0, counts16, fwd="CT", rev="GA",
                   max_position=15, min_alignments=10, min_y_sum=10, want_noise=True):
     """Restatement of counts.py:237-256 on SoA arrays; returns a dict of numpy arrays."""
