@@ -883,7 +883,9 @@ __global__ void test_logp_kernel(int P, const uint32_t* k, const uint32_t* N, Pr
     constexpr int D = ModelDim<MODEL>::value;
     const int lane = threadIdx.x & 31;
     const long long e = blockIdx.x;
+    __shared__ double2 s_prior[64];
     log_table_init();
+    prior_table_init<MODEL>(s_prior, pr, jac);
     if (e >= n_eval) return;
     LaneObs<NPL> ob;
     load_obs<NPL, 32>(ob, k, N, P, mask, lane);
@@ -894,7 +896,7 @@ __global__ void test_logp_kernel(int P, const uint32_t* k, const uint32_t* N, Pr
     for (int j = 0; j < D; ++j) uu[j] = u[e * 4 + j];
     double logp, grad[D], ll[NPL];
     bool valid;
-    eval_model<MODEL, NPL, 32>(ob, uu, jac, pr, (mask == 0 ? 2 * P : P) < NPL * 32, 0xffffffffu, lane, logp, grad, ll, valid);
+    eval_model<MODEL, NPL, 32>(ob, uu, s_prior, pr.phi_min, (mask == 0 ? 2 * P : P) < NPL * 32, 0xffffffffu, lane, logp, grad, ll, valid);
     double sumC = 0.0;
 #pragma unroll
     for (int s = 0; s < NPL; ++s) sumC += logC[s];

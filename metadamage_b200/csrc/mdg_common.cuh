@@ -97,57 +97,60 @@ __device__ __forceinline__ unsigned group_mask() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// FP64 special functions
+// FP64 special functions of the fit kernels.
+//
+// sm_100a FP64 instructions take no constant-bank operand: a full-precision literal costs two
+// register moves (or an LDC) per use, and ptxas, hoisting them, spilled live chain state to make
+// room (round-1 ncu: of ~95 instructions per lgamma/digamma pair only 45 were FP64). A double whose
+// low 32 bits are zero, however, is encoded as an IMMEDIATE. So every polynomial coefficient whose
+// term tolerates a 2^-21 relative perturbation is written as such a 21-significant-bit value
+// (hex-float literals below; the perturbation of the result is stated next to each), exact
+// constants (0.5, 0.25, small integers) are used where the series allows, ln2 is split into
+// immediate pieces, and only four constants (1/12, 1/360, 1/120, ln2_lo) stay full precision.
 // ---------------------------------------------------------------------------------------------
-
-
-
-// ---------------------------------------------------------------------------------------------
-// Fast path special functions of the fit kernels. Coefficients live in constant memory so that
-// the FP64 instructions read them as c[bank][offset] operands (ncu on the first version showed
-// 31 % of all issued instructions were moves materialising FP64 literals).
-// ---------------------------------------------------------------------------------------------
-__constant__ double kLogCoef[9] = {
-    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
-    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
-    6.93147180369123816490e-01, 1.90821492927058770002e-10};
-// Stirling series of lgamma: 1/12, 1/360, 1/1260, 1/1680, 1/1188, 691/360360, 1/156 (alternating signs)
-__constant__ double kStirLg[7] = {1.0 / 12.0, 1.0 / 360.0, 1.0 / 1260.0, 1.0 / 1680.0, 1.0 / 1188.0, 691.0 / 360360.0, 1.0 / 156.0};
-// asymptotic series of digamma: 1/12, 1/120, 1/252, 1/240, 1/132, 691/32760, 1/12
-__constant__ double kStirDg[7] = {1.0 / 12.0, 1.0 / 120.0, 1.0 / 252.0, 1.0 / 240.0, 1.0 / 132.0, 691.0 / 32760.0, 1.0 / 12.0};
+// Stirling series of lgamma  t/12 - t^3/360 + t^5/1260 - t^7/1680 + t^9/1188      (t = 1/y)
+// and of digamma  log y - t/2 - t^2/12 + t^4/120 - t^6/252 + t^8/240 - t^10/132,  y >= 10:
+// truncation 1.9e-14 / 2.1e-14 absolute; the three trailing coefficients of each are immediates
+// (perturbation < 5e-16).
+#define MDG_K_LG2 0x1.a01a0p-11   /* 1/1260 */
+#define MDG_K_LG3 0x1.38138p-11   /* 1/1680 */
+#define MDG_K_LG4 0x1.b951ep-11   /* 1/1188 */
+#define MDG_K_DG2 0x1.04104p-8    /* 1/252 */
+#define MDG_K_DG3 0x1.11111p-8    /* 1/240 */
+#define MDG_K_DG4 0x1.f07c2p-8    /* 1/132 */
 
 // ---------------------------------------------------------------------------------------------
 // Division-free natural log of a positive, normal, finite double.
-//   x = 2^e * m, m in [1, 2);  i = top 7 mantissa bits;  c_i = 1 + (i + 1/2) / 128
-//   r = m / c_i - 1  (|r| <= 2^-8, one fma with the tabulated 1/c_i)
-//   log x = e ln2 + log c_i + (r - r^2/2 + ... - r^6/6)          (r^7/7 < 2e-18)
-// The 2 KB table {1/c_i, log c_i} lives in shared memory (one copy per CTA); every kernel that
-// evaluates logs calls log_table_init() once before use. Absolute error ~1e-17 (relative accuracy
-// degrades only for x within 2^-8 of 1, where the result is < 4e-3 and feeds sums of O(1) terms).
-// The fdlibm-style log it replaces spent 10 of its ~27 FP64 instructions in f / (2 + f).
+//   x = 2^e * m, m in [1, 2);  i = top 8 mantissa bits;  c_i = 1 + (i + 1/2) / 256
+//   r = m / c_i - 1  (|r| <= 2^-9, one fma with the tabulated 1/c_i)
+//   log x = e ln2 + log c_i + (r - r^2/2 + r^3/3 - r^4/4 + r^5/5)        (r^6/6 < 1e-17)
+// 1/3 and 1/5 are immediates (perturbation < 1.2e-15 absolute); e*ln2_hi is exact (21 x 11 bits).
+// The 4 KB table {1/c_i, log c_i} lives in shared memory (one copy per CTA); every kernel that
+// evaluates logs calls log_table_init() once before use.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2* log_table() {
-    __shared__ double2 tab[128];
+    __shared__ double2 tab[256];
     return tab;
 }
 
 __device__ __forceinline__ double* exp_table() {
-    __shared__ double tab[64];  // 2^(j/64)
+    __shared__ double tab[128];  // 2^(j/128)
     return tab;
 }
 
 __device__ __forceinline__ void log_table_init() {
     double2* tab = log_table();
     double* et = exp_table();
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-        const double c = 1.0 + ((double)i + 0.5) / 128.0;
-        tab[i] = make_double2(1.0 / c, log(c));
-        if (i < 64) et[i] = exp2((double)i / 64.0);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const double c = 1.0 + ((double)i + 0.5) / 256.0;
+        const double ic = 1.0 / c;
+        tab[i] = make_double2(ic, -log(ic));   // the log that matches the ROUNDED reciprocal
+        if (i < 128) et[i] = exp2((double)i / 128.0);
     }
     __syncthreads();
 }
 
-// 1/x for positive normal x: hardware seed (rcp.approx, ~2^-23) + two Newton steps (<= 2 ulp)
+// 1/x for positive normal x: hardware seed (MUFU.RCP64H, ~2^-21) + two Newton steps (<= 2 ulp)
 __device__ __forceinline__ double rcp_pos(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -157,38 +160,55 @@ __device__ __forceinline__ double rcp_pos(double x) {
     return fma(r, e, r);
 }
 
-// e^x for any double: x = (64 k + j) ln2/64 + r, |r| <= ln2/128; e^x = 2^k 2^(j/64) e^r with a
-// degree-5 polynomial (r^6/720 < 4e-17). Results below 2^-1000 flush to 0; NaN propagates.
-__device__ __forceinline__ double exp_fast(double x) {
-    const double xc = fmin(fmax(x, -700.0), 709.0);
-    const double n = rint(xc * 92.332482616893656877);               // 64 / ln 2
-    double r = fma(n, -0.01083042469326756, xc);                     // ln2/64, high 32 bits (n * hi is exact)
-    r = fma(n, -2.9815858269852933e-12, r);                          // ln2/64 - hi
-    const int ni = (int)n;
-    const double tj = exp_table()[ni & 63];
-    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    q = fma(r, q, 1.0 / 6.0);
+// e^x for finite |x| <= 708, no range or NaN handling (callers guard):
+//   n = rint(128 x / ln2) by the 1.5*2^52 trick (its low mantissa word IS the integer),
+//   r = x - n ln2/128 with ln2/128 in three immediate pieces (n * piece exact), |r| <= 2.8e-3,
+//   e^x = 2^(n >> 7) * 2^((n & 127)/128) * (1 + r + r^2/2 + r^3/6 + r^4/24 + r^5/120);
+// 1/6, 1/24, 1/120 are immediates (perturbation < 1e-15 relative); the power of two is added
+// straight into the exponent field. ~3 ulp.
+__device__ __forceinline__ double exp_core(double x) {
+    const double nm = fma(x, 0x1.71547p+7, 6755399441055744.0);
+    const int ni = __double2loint(nm);
+    const double n = nm - 6755399441055744.0;
+    double r = fma(n, -0x1.62e42p-8, x);
+    r = fma(n, -0x1.fdf47p-29, r);
+    r = fma(n, -0x1.ef358p-52, r);
+    const double tj = exp_table()[ni & 127];
+    double q = fma(r, 0x1.11111p-7, 0x1.55555p-5);
+    q = fma(r, q, 0x1.55555p-3);
     q = fma(r, q, 0.5);
     q = fma(r, q, 1.0);
     q = fma(r, q, 1.0);
-    const int k = ni >> 6;
-    const double scale = __hiloint2double((k + 1023) << 20, 0);     // k in [-1010, 1023]
-    const double y = (tj * q) * scale;
-    return x != x ? x : (x < -700.0 ? 0.0 : (x > 709.0 ? INFINITY : y));
+    const double y = tj * q;  // in [0.99, 2)
+    return __hiloint2double(__double2hiint(y) + ((ni >> 7) << 20), __double2loint(y));
+}
+
+// e^x for x <= 0 (sign bit set or +0; -inf and NaN-with-sign allowed): arguments below -700 act
+// as -700.99 (one integer min on the high word), i.e. the result is ~1e-305 instead of 0.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const unsigned hi = (unsigned)__double2hiint(x);
+    return exp_core(__hiloint2double((int)min(hi, 0xc085e000u), __double2loint(x)));
+}
+
+// e^x for any double (tests, cold callers): exact limits, NaN propagates
+__device__ __forceinline__ double exp_fast(double x) {
+    const double xc = fmin(fmax(x, -700.0), 700.0);
+    const double y = exp_core(xc);
+    return x != x ? x : (x < -700.0 ? (x < -745.2 ? 0.0 : exp(x)) : (x > 700.0 ? exp(x) : y));
 }
 
 __device__ __forceinline__ double log_pos(double x) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
+    const double2 t = log_table()[(hi >> 12) & 255];
     const double de = (double)((hi >> 20) - 1023);
-    const double2 t = log_table()[(hi >> 13) & 127];
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, t.x, -1.0);
-    double q = fma(r, -1.0 / 6.0, 1.0 / 5.0);
-    q = fma(r, q, -1.0 / 4.0);
-    q = fma(r, q, 1.0 / 3.0);
-    q = fma(r, q, -1.0 / 2.0);
+    double q = fma(r, 0x1.9999ap-3, -0.25);
+    q = fma(r, q, 0x1.55555p-2);
+    q = fma(r, q, -0.5);
     q = fma(r, q, 1.0);
-    return fma(de, kLogCoef[7], t.y) + fma(de, kLogCoef[8], r * q);
+    // ln2 = 0x1.62e43p-1 - 1.904654299957768e-09
+    return fma(de, 0x1.62e43p-1, t.y) + fma(de, -1.904654299957768e-09, r * q);
 }
 
 // two standard normals (Box-Muller); sincospi needs no large-argument reduction
@@ -210,7 +230,7 @@ __device__ MDG_COLD double exp_cold(double x) { return exp(x); }
 __device__ MDG_COLD double log_cold(double x) { return log(x); }
 __device__ MDG_COLD double sigmoid_cold(double x) { return 1.0 / (1.0 + exp(-x)); }
 
-// st = lgamma(y) - 0.5 log(2 pi) and dg = digamma(y) for y >= 10 (7 Bernoulli terms each)
+// st = lgamma(y) - 0.5 log(2 pi) and dg = digamma(y) for y >= 10, t = 1/y (5 Bernoulli terms each)
 __device__ __forceinline__ double log_sel(double x) {
 #if MDG_LOGFN
     return log_pos(x);
@@ -222,38 +242,56 @@ __device__ __forceinline__ double log_sel(double x) {
 __device__ __forceinline__ void stirling(double y, double t, double& st, double& dg) {
     const double L = log_sel(y);
     const double t2 = t * t;
-    double sl = fma(t2, -kStirLg[6], kStirLg[5]);
-    sl = fma(t2, -sl, kStirLg[4]);
-    sl = fma(t2, -sl, kStirLg[3]);
-    sl = fma(t2, -sl, kStirLg[2]);
-    sl = fma(t2, -sl, kStirLg[1]);
-    sl = fma(t2, -sl, kStirLg[0]);
-    double sd = fma(t2, -kStirDg[6], kStirDg[5]);
-    sd = fma(t2, -sd, kStirDg[4]);
-    sd = fma(t2, -sd, kStirDg[3]);
-    sd = fma(t2, -sd, kStirDg[2]);
-    sd = fma(t2, -sd, kStirDg[1]);
-    sd = fma(t2, -sd, kStirDg[0]);
+    double sl = fma(t2, -MDG_K_LG4, MDG_K_LG3);
+    sl = fma(t2, -sl, MDG_K_LG2);
+    sl = fma(t2, -sl, 1.0 / 360.0);
+    sl = fma(t2, -sl, 1.0 / 12.0);
+    double sd = fma(t2, -MDG_K_DG4, MDG_K_DG3);
+    sd = fma(t2, -sd, MDG_K_DG2);
+    sd = fma(t2, -sd, 1.0 / 120.0);
+    sd = fma(t2, -sd, 1.0 / 12.0);
     st = fma(t, sl, fma(y - 0.5, L, -y));
     dg = fma(-t2, sd, fma(-0.5, t, L));
 }
 
-// lgamma(x) and digamma(x), x > 0, in one pass. x < 10 is shifted to y = x + 10 with the product
-// P = x (x+1) ... (x+9) and its derivative P' (lgamma(x) = lgamma(y) - log P, digamma(x) =
-// digamma(y) - P'/P: one log and one division instead of ten); y >= 10 uses the Stirling /
-// asymptotic series with 7 Bernoulli terms (truncation < 4e-17 absolute at y = 10).
+// P(x) = x (x+1) ... (x+9) and P'(x) by Horner on the expanded polynomials: every coefficient is an
+// integer below 2^22 with at most 21 significant bits, i.e. an exact immediate; all terms are
+// positive for x > 0, so there is no cancellation (two independent chains of 10 and 9 operations
+// instead of the 27 of the running product).
+__device__ __forceinline__ void shift_poly10(double x, double& P, double& dP) {
+    double p = x + 45.0;
+    p = fma(x, p, 870.0);
+    p = fma(x, p, 9450.0);
+    p = fma(x, p, 63273.0);
+    p = fma(x, p, 269325.0);
+    p = fma(x, p, 723680.0);
+    p = fma(x, p, 1172700.0);
+    p = fma(x, p, 1026576.0);
+    p = fma(x, p, 362880.0);
+    P = x * p;
+    double q = fma(x, 10.0, 405.0);
+    q = fma(x, q, 6960.0);
+    q = fma(x, q, 66150.0);
+    q = fma(x, q, 379638.0);
+    q = fma(x, q, 1346625.0);
+    q = fma(x, q, 2894720.0);
+    q = fma(x, q, 3518100.0);
+    q = fma(x, q, 2053152.0);
+    dP = fma(x, q, 362880.0);
+}
+
+// lgamma(x) - 0.5 log(2 pi) and digamma(x), x > 0, in one pass. x < 10 is shifted to y = x + 10
+// with P = x (x+1) ... (x+9) and its derivative (lgamma(x) = lgamma(y) - log P, digamma(x) =
+// digamma(y) - P'/P: one log and one reciprocal instead of ten); y >= 10 uses the Stirling /
+// asymptotic series. The constant 0.5 log(2 pi) is left out: it cancels in the beta-binomial
+// log-likelihood (three lgammas enter with +, three with -).
 __device__ __forceinline__ void lgam_digam_u(double x, unsigned gmask, double& lg, double& dg) {
     double y = x, logP = 0.0, dP = 0.0;
     const bool small = x < 10.0;
     double t;
     if (small) {
-        double P = x, Q = 1.0;
-#pragma unroll
-        for (int i = 1; i < 10; ++i) {
-            const double xi = x + (double)i;
-            Q = fma(Q, xi, P);
-            P *= xi;
-        }
+        double P, Q;
+        shift_poly10(x, P, Q);
         logP = log_sel(P);
         y = x + 10.0;
         const double r = rcp_pos(y * P);  // one reciprocal serves 1/y and Q/P
@@ -264,29 +302,16 @@ __device__ __forceinline__ void lgam_digam_u(double x, unsigned gmask, double& l
     }
     double st, d;
     stirling(y, t, st, d);
-    lg = (st + 0.91893853320467274178) - logP;
+    lg = st - logP;
     dg = d - dP;
 }
 
 // single-thread forms (log C(N,k), the predictive's BTRS sampler, the special-function test hook)
 __device__ __forceinline__ void lgam_digam(double x, double& lg, double& dg) {
-    double y = x, logP = 0.0, dP = 0.0;
-    if (x < 10.0) {
-        double P = x, Q = 1.0;
-#pragma unroll
-        for (int i = 1; i < 10; ++i) {
-            const double xi = x + (double)i;
-            Q = fma(Q, xi, P);
-            P *= xi;
-        }
-        logP = log_sel(P);
-        dP = Q / P;
-        y = x + 10.0;
-    }
-    double st, d;
-    stirling(y, rcp_pos(y), st, d);
-    lg = (st + 0.91893853320467274178) - logP;
-    dg = d - dP;
+    double a, b;
+    lgam_digam_u(x, 0xffffffffu, a, b);
+    lg = a + 0.91893853320467274178;
+    dg = b;
 }
 
 __device__ __forceinline__ double lgam(double x) {

@@ -125,15 +125,13 @@ __global__ void __launch_bounds__(kCountsThreads, MDG_COUNTS_MINBLOCKS) counts_r
     uint8_t* s_kept = o_head + cap;
     uint32_t* s_dense = reinterpret_cast<uint32_t*>(s_kept + cap);  // [warps][2][2P]
     __shared__ uint64_t s_bar;
-    __shared__ unsigned int s_tile;
     __shared__ int s_warp_cnt[kCountsWarps];
     __shared__ int s_nseg, s_nowned, s_kept_total;
     __shared__ long long s_base;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { s_tile = atomicAdd(p.tile_ticket, 1u); s_nowned = 0; }
-    __syncthreads();
-    const unsigned tile = s_tile;
+    if (tid == 0) s_nowned = 0;  // (made visible by the barrier that ends the staging step)
+    const unsigned tile = blockIdx.x;  // tiles are independent: no ticket, no ordering between CTAs
     const long long row0 = (long long)tile * p.T;
     const long long remaining = p.n_rows - row0;
     const int nload = (int)(remaining < cap ? remaining : cap);

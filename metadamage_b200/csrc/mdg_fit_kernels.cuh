@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
     __shared__ GroupShared<D> sh_all[WARPS * GROUPS];
     __shared__ WarpLanes<NPL> sh_lanes[WARPS];
     __shared__ unsigned int sh_item[WARPS];
+    __shared__ double2 sh_prior[64];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / GW, lig = lane % GW;
@@ -150,6 +151,8 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
     const int max_depth = p.cfg.max_tree_depth < kMaxTreeDepth ? p.cfg.max_tree_depth : kMaxTreeDepth;
     const double log_target_heur = -0.22314355131420976;  // log(0.8)
     log_table_init();
+    prior_table_init<MODEL>(sh_prior, p.pr, 1);
+    const double phi_min = p.pr.phi_min;
 
     for (;;) {
         if (lane == 0) sh_item[warp] = atomicAdd(p.work_counter, 1u);
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                 for (int j = 0; j < D; ++j) { rh[j] = fma(-0.5 * e, gf[j], rf[j]); zn[j] = fma(e * imm[j], rh[j], zf[j]); }
                 double logp, grad[D], ll_leaf[NPL];
                 bool valid;
-                eval_model<MODEL, NPL, GW>(ob, zn, 1, p.pr, has_spare, gmask, lig, logp, grad, ll_leaf, valid);
+                eval_model<MODEL, NPL, GW>(ob, zn, sh_prior, phi_min, has_spare, gmask, lig, logp, grad, ll_leaf, valid);
                 ++n_grad;
                 pen = valid ? -logp : nan("");
 #pragma unroll
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                     if (isnan(dE)) dE = INFINITY;
                     const double leaf_w = -dE;
                     const bool leaf_div = dE > p.cfg.max_delta_energy;
-                    const double leaf_acc = fmin(1.0, exp_fast(-dE));
+                    const double leaf_acc = dE <= 0.0 ? 1.0 : exp_nonpos(-dE);  // min(1, e^-dE); dE is never NaN here
                     const int leaf_idx = s_nprop;
                     bool take;
                     if (leaf_idx == 0) {
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                         uniform2(philox4x32(key, leaf_counter, (uint32_t)t, c2word(run_kind, P_SUB), 0u), us, unused);
                         // expit(d) and logaddexp share one exponential: e = exp(-|d|)
                         const double dlt = leaf_w - s_weight;
-                        const double ed = exp_fast(-fabs(dlt));
+                        const double ed = exp_nonpos(-fabs(dlt));  // NaN -> ~0 -> take = false
                         const double inv = rcp_pos(1.0 + ed);
                         const double prob = dlt >= 0.0 ? inv : ed * inv;
                         take = us < prob;  // NaN -> false
@@ -391,8 +394,10 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                     } else {
                         // ---- subtree finished: _combine_tree(..., biased_transition=True) ----
                         const double dlt_m = s_weight - m_weight;
-                        const double pm = exp_fast(dlt_m);
-                        const double prob = (turning || s_div) ? 0.0 : pm;
+                        // min(1, e^d) and logaddexp share one exponential e^-|d| (u_main < 1, so a
+                        // probability above 1 acts as 1; NaN -> ~0 -> false)
+                        const double em = exp_nonpos(-fabs(dlt_m));
+                        const double prob = (turning || s_div) ? 0.0 : (dlt_m >= 0.0 ? 1.0 : em);
                         const bool take_main = u_main < prob;
                         __syncwarp(gmask);
                         if (lig == 0) {
@@ -418,8 +423,8 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                             for (int s = 0; s < NPL; ++s) ll_main[s] = ll_sub[s];
                         }
                         m_depth += 1;
-                        // logaddexp(m_weight, s_weight) = max + log(1 + exp(-|d|)), with exp(-|d|) from exp(d) above
-                        m_weight = isnan(dlt_m) ? -INFINITY : fmax(m_weight, s_weight) + log_pos(1.0 + (dlt_m <= 0.0 ? pm : 1.0 / pm));
+                        // logaddexp(m_weight, s_weight) = max + log(1 + e^-|d|)
+                        m_weight = isnan(dlt_m) ? -INFINITY : fmax(m_weight, s_weight) + log_pos(1.0 + em);
                         m_div = s_div;
                         m_sum_acc += s_sum_acc;
                         m_nprop += s_nprop;
@@ -663,7 +668,7 @@ __device__ __forceinline__ bool chol_solve(const double (&H)[D][D], const double
 
 template <int MODEL, int NPL>
 __device__ void map_fit_group(const LaneObs<NPL>& ob, const double (&logC)[NPL], int P, const Priors& pr,
-                              bool has_spare, int lig, MapRecord& out) {
+                              const double2* ptab, bool has_spare, int lig, MapRecord& out) {
     constexpr int D = ModelDim<MODEL>::value;
     constexpr unsigned gmask = 0xffffffffu;
     constexpr double UMAX = 40.0;
@@ -701,7 +706,7 @@ __device__ void map_fit_group(const LaneObs<NPL>& ob, const double (&logC)[NPL],
     }
     double f, g[D], ll[NPL], lp;
     bool ok;
-    eval_model<MODEL, NPL, 32>(ob, u, 0, pr, has_spare, gmask, lig, lp, g, ll, ok);
+    eval_model<MODEL, NPL, 32>(ob, u, ptab, pr.phi_min, has_spare, gmask, lig, lp, g, ll, ok);
     // f carries log C(N,k) so that its magnitude (and the step-acceptance slack) matches the
     // constrained-space log posterior; `slack` covers the cancellation noise of the lgamma sums
     double sumC = 0.0, scale = 0.0;
@@ -733,8 +738,8 @@ __device__ void map_fit_group(const LaneObs<NPL>& ob, const double (&logC)[NPL],
             bool okp, okm;
 #pragma unroll
             for (int i = 0; i < D; ++i) { up[i] = u[i] + (i == j ? h : 0.0); um[i] = u[i] - (i == j ? h : 0.0); }
-            eval_model<MODEL, NPL, 32>(ob, up, 0, pr, has_spare, gmask, lig, t0, gp, ll, okp);
-            eval_model<MODEL, NPL, 32>(ob, um, 0, pr, has_spare, gmask, lig, t1, gm, ll, okm);
+            eval_model<MODEL, NPL, 32>(ob, up, ptab, pr.phi_min, has_spare, gmask, lig, t0, gp, ll, okp);
+            eval_model<MODEL, NPL, 32>(ob, um, ptab, pr.phi_min, has_spare, gmask, lig, t1, gm, ll, okm);
 #pragma unroll
             for (int i = 0; i < D; ++i) H[i][j] = (okp && okm) ? -(gp[i] - gm[i]) / (2.0 * h) : (i == j ? 1.0 : 0.0);
         }
@@ -760,7 +765,7 @@ __device__ void map_fit_group(const LaneObs<NPL>& ob, const double (&logC)[NPL],
                 dmax = fmax(dmax, fabs(un[i] - u[i]));
             }
             bool okn;
-            eval_model<MODEL, NPL, 32>(ob, un, 0, pr, has_spare, gmask, lig, lpn, gn, ll, okn);
+            eval_model<MODEL, NPL, 32>(ob, un, ptab, pr.phi_min, has_spare, gmask, lig, lpn, gn, ll, okn);
             if (okn && -(lpn + sumC) <= f + slack) {
                 double gmax = 0.0;
 #pragma unroll
@@ -789,8 +794,11 @@ __device__ void map_fit_group(const LaneObs<NPL>& ob, const double (&logC)[NPL],
 template <int NPL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) map_kernel(const MapLaunch p) {
     __shared__ unsigned int sh_item[WARPS];
+    __shared__ double2 sh_prior[2][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     log_table_init();
+    prior_table_init<0>(sh_prior[0], p.pr, 0);
+    prior_table_init<1>(sh_prior[1], p.pr, 0);
     for (;;) {
         if (lane == 0) sh_item[warp] = atomicAdd(p.work_counter, 1u);
         __syncwarp();
@@ -804,8 +812,8 @@ __global__ void __launch_bounds__(WARPS * 32) map_kernel(const MapLaunch p) {
         log_binom_coeff<NPL>(ob, logC);
         const bool has_spare = 2 * p.P < NPL * 32;
         MapRecord rec;
-        if (model == 0) map_fit_group<0, NPL>(ob, logC, p.P, p.pr, has_spare, lane, rec);
-        else map_fit_group<1, NPL>(ob, logC, p.P, p.pr, has_spare, lane, rec);
+        if (model == 0) map_fit_group<0, NPL>(ob, logC, p.P, p.pr, sh_prior[0], has_spare, lane, rec);
+        else map_fit_group<1, NPL>(ob, logC, p.P, p.pr, sh_prior[1], has_spare, lane, rec);
         if (lane == 0) p.rec[item] = rec;
     }
 }

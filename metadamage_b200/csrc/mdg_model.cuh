@@ -53,59 +53,82 @@ __device__ __forceinline__ void log_binom_coeff(const LaneObs<NPL>& ob, double (
         logC[s] = ob.act[s] ? lgam(ob.N[s] + 1.0) - lgam(ob.k[s] + 1.0) - lgam(ob.N[s] - ob.k[s] + 1.0) : 0.0;
 }
 
-// Evaluate log p(y | theta(u)) + log prior(theta(u)) [+ log |d theta / d u| if jac] and its
-// gradient w.r.t. u, for the group's chain. `ll[s]` is the per-position log-likelihood WITHOUT
-// log C(N,k). `valid` is false where the reference would produce NaN (clip(Dz,0,1) reaching 1,
-// fits.py:50) or anything is non-finite. `has_spare`: the group's last slot is inactive (k = N = 0),
-// so its evaluations are exactly the position-independent lgamma(phi) [null: also lgamma(alpha),
-// lgamma(beta)] that every lane needs: they are broadcast instead of being computed again.
-template <int MODEL, int NPL, int GW>
-__device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double (&u)[ModelDim<MODEL>::value],
-                                           int jac, const Priors& pr, bool has_spare, unsigned gmask, int lig,
-                                           double& logp, double (&grad)[ModelDim<MODEL>::value],
-                                           double (&ll)[NPL], bool& valid) {
+// Per-lane coefficients of the prior (+ Jacobian) term: lane j < D owns parameter j and contributes
+//   c0 + c1 u + c2 softplus(u) + c3 e^u
+// to the log density, hence c1 + c2 sigmoid(u) + c3 e^u to d/du_j:
+//   Beta(a, b) on sigmoid(u):  log p = (a-1+jac)(u - sp) - (b-1+jac) sp - log B(a,b)
+//                              -> c0 = -log B, c1 = a-1+jac, c2 = -(a+b-2+2 jac), c3 = 0
+//   Exponential(rate) on e^u:  log p = log rate - rate e^u + jac u
+//                              -> c0 = log rate, c1 = jac, c2 = 0, c3 = -rate
+// Lanes >= D carry zeros. The table ([2][32] double2, conflict-free 128-bit loads) lives in shared
+// memory and is filled once per CTA by prior_table_init.
+template <int MODEL>
+__device__ __forceinline__ void prior_table_init(double2* tab, const Priors& pr, int jac) {
     constexpr int D = ModelDim<MODEL>::value;
     const double dj = (double)jac;
+    for (int l = threadIdx.x; l < 32; l += blockDim.x) {
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        if (l < D - 1) {
+            double a = pr.qa, b = pr.qb, nlb = pr.nlb_q;
+            if (MODEL == 0 && l == 1) { a = pr.Aa; b = pr.Ab; nlb = pr.nlb_A; }
+            if (MODEL == 0 && l == 2) { a = pr.ca; b = pr.cb; nlb = pr.nlb_c; }
+            c0 = nlb; c1 = a - 1.0 + dj; c2 = -((a - 1.0 + dj) + (b - 1.0 + dj));
+        } else if (l == D - 1) {
+            c0 = pr.log_rate; c1 = dj; c3 = -pr.rate;
+        }
+        tab[l] = make_double2(c0, c1);
+        tab[32 + l] = make_double2(c2, c3);
+    }
+    __syncthreads();
+}
+
+// Evaluate log p(y | theta(u)) + log prior(theta(u)) [+ log |d theta / d u| if the prior table was
+// built with jac] and its gradient w.r.t. u, for the group's chain. `ll[s]` is the per-position
+// log-likelihood WITHOUT log C(N,k). `valid` is false where the reference would produce NaN
+// (clip(Dz,0,1) reaching 1, fits.py:50), where |u_j| >= 700 (e^u or the sigmoid saturate; also
+// catches NaN/inf states) or anything is non-finite. `has_spare`: the group's last slot is
+// inactive (k = N = 0), so its evaluations are exactly the position-independent lgamma(phi) [null:
+// also lgamma(alpha), lgamma(beta)] that every lane needs: they are broadcast instead of being
+// computed again.
+template <int MODEL, int NPL, int GW>
+__device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double (&u)[ModelDim<MODEL>::value],
+                                           const double2* __restrict__ ptab, double phi_min, bool has_spare,
+                                           unsigned gmask, int lig, double& logp,
+                                           double (&grad)[ModelDim<MODEL>::value], double (&ll)[NPL], bool& valid) {
+    constexpr int D = ModelDim<MODEL>::value;
 
     // --- group-uniform transforms, one parameter per lane, then broadcast --------------------
     double myu = u[0];
 #pragma unroll
     for (int j = 1; j < D; ++j) myu = (lig == j) ? u[j] : myu;
-    double e = exp_fast(-fabs(myu));
-    double l1p = log_pos(1.0 + e);  // absolute accuracy 1e-17 is all the log-density needs
-    double inv = rcp_pos(1.0 + e);
-    double sp = fmax(myu, 0.0) + l1p;             // softplus(u)
-    double sg = (myu >= 0.0) ? inv : e * inv;     // sigmoid(u)
-    double ex = exp_fast(myu);                      // exp(u)
-    // this lane's prior (+ Jacobian) term of the log density
-    double lp_lane = 0.0;
-    {
-        double a = pr.qa, b = pr.qb, nlb = pr.nlb_q;
-        if (MODEL == 0) {
-            if (lig == 1) { a = pr.Aa; b = pr.Ab; nlb = pr.nlb_A; }
-            if (lig == 2) { a = pr.ca; b = pr.cb; nlb = pr.nlb_c; }
-        }
-        double beta_term = (a - 1.0 + dj) * (myu - sp) + (b - 1.0 + dj) * (-sp) + nlb;
-        double exp_term = pr.log_rate - pr.rate * ex + dj * myu;
-        lp_lane = (lig < D - 1) ? beta_term : (lig == D - 1 ? exp_term : 0.0);
-    }
+    const bool in_range = fabs(myu) < 700.0;  // false for NaN
+    // ONE exponential per lane: e^-|u| for the sigmoid lanes, e^u for the phi lane
+    const double E = exp_core(lig == D - 1 ? myu : -fabs(myu));
+    const double l1p = log_pos(1.0 + E);
+    const double inv = rcp_pos(1.0 + E);
+    const double sp = fmax(myu, 0.0) + l1p;             // softplus(u)
+    const double sg = (myu >= 0.0) ? inv : E * inv;     // sigmoid(u)
+    // this lane's prior (+ Jacobian) term of the log density and of the gradient
+    const double2 c01 = ptab[lig], c23 = ptab[32 + lig];
+    const double lp_lane = fma(c23.y, E, fma(c23.x, sp, fma(c01.y, myu, c01.x)));
+    const double gp_lane = fma(c23.y, E, fma(c23.x, sg, c01.y));
     const double q = __shfl_sync(gmask, sg, 0, GW);
     const double log1mq = -__shfl_sync(gmask, sp, 0, GW);
-    const double delta = __shfl_sync(gmask, ex, D - 1, GW);
+    const double delta = __shfl_sync(gmask, E, D - 1, GW);
     double A = 0.0, c = 0.0;
     if (MODEL == 0) {
         A = __shfl_sync(gmask, sg, 1, GW);
         c = __shfl_sync(gmask, sg, 2, GW);
     }
-    const double phi = delta + pr.phi_min;
+    const double phi = delta + phi_min;
 
     // --- per-position special functions -------------------------------------------------------
     double lg1[NPL], lg2[NPL], lg3[NPL], dg1[NPL], dg2[NPL], dg3[NPL];
     double lga[NPL], lgb[NPL], dga[NPL], dgb[NPL], Dz[NPL], w[NPL];
-    bool bad = false;
+    bool bad = !in_range;
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
-        w[s] = (MODEL == 0) ? exp_fast(ob.x[s] * log1mq) : 1.0;
+        w[s] = (MODEL == 0) ? exp_nonpos(ob.x[s] * log1mq) : 1.0;
         double Dv = (MODEL == 0) ? fma(A, w[s], c) : q;
         bool ok = (Dv > 0.0) && (Dv < 1.0);
         bad |= (!ok) && ob.act[s];
@@ -176,16 +199,14 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
 
     // --- chain rule to the unconstrained parameters ----------------------------------------------
     logp = s_ll;
-    const double gq_prior = (pr.qa - 1.0 + dj) * (1.0 - q) - (pr.qb - 1.0 + dj) * q;
-    const double gd_prior = -pr.rate * delta + dj;
     if (MODEL == 0) {
-        grad[0] = fma(-A * q, s_dDxw, gq_prior);
-        grad[1] = fma(A * (1.0 - A), s_dDw, (pr.Aa - 1.0 + dj) * (1.0 - A) - (pr.Ab - 1.0 + dj) * A);
-        grad[2] = fma(c * (1.0 - c), s_dD, (pr.ca - 1.0 + dj) * (1.0 - c) - (pr.cb - 1.0 + dj) * c);
-        grad[3] = fma(delta, s_dphi, gd_prior);
+        grad[0] = fma(-A * q, s_dDxw, __shfl_sync(gmask, gp_lane, 0, GW));
+        grad[1] = fma(A * (1.0 - A), s_dDw, __shfl_sync(gmask, gp_lane, 1, GW));
+        grad[2] = fma(c * (1.0 - c), s_dD, __shfl_sync(gmask, gp_lane, 2, GW));
+        grad[3] = fma(delta, s_dphi, __shfl_sync(gmask, gp_lane, 3, GW));
     } else {
-        grad[0] = fma(q * (1.0 - q), s_dD, gq_prior);
-        grad[1] = fma(delta, s_dphi, gd_prior);
+        grad[0] = fma(q * (1.0 - q), s_dD, __shfl_sync(gmask, gp_lane, 0, GW));
+        grad[1] = fma(delta, s_dphi, __shfl_sync(gmask, gp_lane, 1, GW));
     }
     bool fin = isfinite(logp);
 #pragma unroll

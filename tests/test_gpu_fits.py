@@ -42,20 +42,21 @@ def test_special_functions(ctx):
 
 
 def test_fast_exp_and_log(ctx):
-    """The kernels' table-driven exp / log: a few ulp relative for exp, 1e-16 absolute-ish for log."""
+    """The kernels' table-driven exp / log with immediate-encoded coefficients (csrc/mdg_common.cuh):
+    a few ulp relative for exp, ~1e-15 absolute-ish for log (1/3 and 1/5 carry 21 significant bits)."""
     rng = np.random.default_rng(4)
     x = np.concatenate([rng.uniform(-700, 700, 20000), rng.uniform(-2, 2, 20000), [0.0, -0.0, 1e-300, -745.0, -800.0, 709.0, 710.0, np.inf, -np.inf]])
     ex, _ = ctx.exp_log(x)
     ref = np.exp(x)
     fin = np.isfinite(ref) & (ref > 1e-300)
-    assert np.max(np.abs(ex[fin] - ref[fin]) / ref[fin]) < 2e-15
+    assert np.max(np.abs(ex[fin] - ref[fin]) / ref[fin]) < 4e-15
     assert ex[x == -np.inf][0] == 0.0 and np.isinf(ex[x == np.inf][0]) and ex[x == -800.0][0] == 0.0
     assert np.isnan(ctx.exp_log(np.array([np.nan]))[0][0])
     y = np.concatenate([10.0 ** rng.uniform(-300, 300, 20000), rng.uniform(0.5, 2.0, 20000), [1.0, 2.0, 0.5, 10.0]])
     _, lg = ctx.exp_log(y)
     ref = np.log(y)
-    assert np.max(np.abs(lg - ref) / np.maximum(1.0, np.abs(ref))) < 4e-16
-    assert abs(lg[y == 1.0][0]) < 1e-16
+    assert np.max(np.abs(lg - ref) / np.maximum(1.0, np.abs(ref))) < 2e-15
+    assert abs(lg[y == 1.0][0]) < 2e-15
 
 
 @pytest.mark.parametrize("P", [15, 25, 40])
