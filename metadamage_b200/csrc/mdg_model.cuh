@@ -135,12 +135,18 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
         Dv = ok ? Dv : 0.5;
         Dz[s] = Dv;
         double al = Dv * phi, be = (1.0 - Dv) * phi;
-        lgam_digam_u(ob.k[s] + al, gmask, lg1[s], dg1[s]);
-        lgam_digam_u(ob.N[s] - ob.k[s] + be, gmask, lg2[s], dg2[s]);
-        lgam_digam_u(ob.N[s] + phi, gmask, lg3[s], dg3[s]);
         if (MODEL == 0) {
-            lgam_digam_u(al, gmask, lga[s], dga[s]);
-            lgam_digam_u(be, gmask, lgb[s], dgb[s]);
+            const double xs[5] = {ob.k[s] + al, ob.N[s] - ob.k[s] + be, ob.N[s] + phi, al, be};
+            double l5[5], d5[5];
+            lgam_digam_batch<5>(xs, gmask, l5, d5);
+            lg1[s] = l5[0]; lg2[s] = l5[1]; lg3[s] = l5[2]; lga[s] = l5[3]; lgb[s] = l5[4];
+            dg1[s] = d5[0]; dg2[s] = d5[1]; dg3[s] = d5[2]; dga[s] = d5[3]; dgb[s] = d5[4];
+        } else {
+            const double xs[3] = {ob.k[s] + al, ob.N[s] - ob.k[s] + be, ob.N[s] + phi};
+            double l3[3], d3[3];
+            lgam_digam_batch<3>(xs, gmask, l3, d3);
+            lg1[s] = l3[0]; lg2[s] = l3[1]; lg3[s] = l3[2];
+            dg1[s] = d3[0]; dg2[s] = d3[1]; dg3[s] = d3[2];
         }
     }
     // position-independent pieces: the spare slot (k = N = 0) has just evaluated them

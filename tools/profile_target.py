@@ -17,7 +17,7 @@ samp = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 dev = torch.device("cuda", 0)
 ctx = Context(0)
 ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-r = bench.counts_stress(ctx, torch, dev, reps=1)
+r = bench.counts_stress(ctx, torch, dev, reps=int(os.environ.get("MDG_COUNTS_REPS", "1")))
 print("counts", r["kernel_ms"], "ms", r["achieved"], "GB/s")
 tid, k, N, g = syn.dense_fit_batch(n_fit)
 out = ctx.fit_batch(tid, k, N, _lib.default_config(num_warmup=warm, num_samples=samp))
