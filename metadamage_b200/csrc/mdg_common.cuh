@@ -11,7 +11,8 @@
 #define MDG_LOGFN 1          // 1: table-driven log_pos; 0: CUDA log()
 #endif
 #ifndef MDG_COLD_INLINE
-#define MDG_COLD_INLINE 1    // 1: everything inlined; 0: cold helpers (Philox, Box-Muller, logaddexp, ...) out of line
+#define MDG_COLD_INLINE 0    // 0: one out-of-line copy of Philox, Box-Muller, logaddexp, cold exp/log (the hot loop is
+                             // instruction-fetch sensitive: -9 % NUTS time); 1: everything inlined
 #endif
 #if MDG_COLD_INLINE
 #define MDG_COLD __forceinline__

@@ -15,6 +15,9 @@
 
 namespace mdg {
 
+#ifndef MDG_PARK
+#define MDG_PARK 1
+#endif
 constexpr int kMaxTreeDepth = 10;
 constexpr int kMaxWindows = 16;
 
@@ -62,6 +65,11 @@ struct GroupShared {
     double da_x, da_xavg, da_gavg, da_prox, mean_accept, h_step, h_Er;
     double m_weight, m_sum_acc, m_pe_p, u_main, pe_cur, eps, s_pe_p;
     double m_rsum[D];
+#if MDG_PARK
+    // group-uniform values that are live ACROSS the gradient evaluation but not used inside it:
+    // parked here so that the evaluation's five interleaved special-function chains get the registers
+    double imm[D], s_rsum[D], zn_park[D], rh_park[D], E0, s_weight, s_sum_acc;
+#endif
     int da_t, wf_n, window_idx, h_last, h_dir, m_nprop;
     uint32_t h_att, h_call, init_attempt, n_div;
 };
@@ -183,7 +191,11 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
         }
 
         // ---- hot chain state in registers (group-uniform unless noted) ----
+#if MDG_PARK
+        double (&imm)[D] = sh.imm;
+#else
         double imm[D];
+#endif
 #pragma unroll
         for (int j = 0; j < D; ++j) imm[j] = 1.0;
         double ll_sub[NPL];  // per lane
@@ -191,11 +203,16 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
         for (int s = 0; s < NPL; ++s) ll_sub[s] = 0.0;
         uint32_t n_grad = 0;
         int failed = 0;
+#if MDG_PARK
+        double& E0 = sh.E0; double (&s_rsum)[D] = sh.s_rsum; double& s_weight = sh.s_weight; double& s_sum_acc = sh.s_sum_acc;
+        E0 = 0.0; s_weight = 0.0; s_sum_acc = 0.0;
+#else
         double E0 = 0.0;
         double s_rsum[D];
+        double s_weight = 0.0, s_sum_acc = 0.0;
+#endif
         int m_depth = 0;
         bool m_turning = false, m_div = false, going_right = true;
-        double s_weight = 0.0, s_sum_acc = 0.0;
         int s_nprop = 0;
         bool s_div = false;
         uint32_t leaf_counter = 0;
@@ -317,7 +334,16 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                 for (int j = 0; j < D; ++j) { rh[j] = fma(-0.5 * e, gf[j], rf[j]); zn[j] = fma(e * imm[j], rh[j], zf[j]); }
                 double logp, grad[D], ll_leaf[NPL];
                 bool valid;
+#if MDG_PARK
+#pragma unroll
+                for (int j = 0; j < D; ++j) { sh.zn_park[j] = zn[j]; sh.rh_park[j] = rh[j]; }
+#endif
                 eval_model<MODEL, NPL, GW>(ob, zn, sh_prior, phi_min, has_spare, gmask, lig, logp, grad, ll_leaf, valid);
+#if MDG_PARK
+                __syncwarp(gmask);  // (compiler barrier: the parked values are re-read, not kept in registers)
+#pragma unroll
+                for (int j = 0; j < D; ++j) { zn[j] = sh.zn_park[j]; rh[j] = sh.rh_park[j]; }
+#endif
                 ++n_grad;
                 pen = valid ? -logp : nan("");
 #pragma unroll
