@@ -647,10 +647,18 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const 
     const Priors pr = make_priors(*cfg);
     MDG_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
-    const long long chunk_cap = 16384;
-    const long long chunk_max = std::min<long long>(n_tax, chunk_cap);
     const int sample_runs = out_samples ? MDG_NUM_RUNS : (fwd_rev ? 3 : 1);
     const int items_per_tax = R + (fwd_rev ? 2 : 0);
+    // TaxIDs per chunk: every chunk ends with the tail of its four NUTS launches, so chunks are as
+    // large as ~8 GB of scratch allows (posterior draws dominate: 96 KB per TaxID at S = 1000)
+    long long chunk_cap = 65536;
+    {
+        const size_t per_tax = (size_t)sample_runs * S * 4 * 8 + (size_t)MDG_NUM_RUNS * (sizeof(RunRecord) + 2 * R * 8) +
+                               (size_t)items_per_tax * 3 * 8 + 2 * sizeof(MapRecord);
+        while (chunk_cap > 4096 && (size_t)chunk_cap * per_tax > ((size_t)8 << 30)) chunk_cap /= 2;
+        if (const char* e = getenv("MDG_FIT_CHUNK")) { const long long v = atoll(e); if (v >= 1 && v <= (1 << 20)) chunk_cap = v; }  // tests
+    }
+    const long long chunk_max = std::min<long long>(n_tax, chunk_cap);
 
     // ---- device buffers ----
     // persistent scratch (per chunk)
@@ -750,25 +758,27 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const 
         MDG_CUDA_TRY(cudaEventRecord(ctx->fork_ev, st));
         for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0));
         {
+            // Launch order = dispatch order of the persistent CTAs: the kernels share the SMs as CTAs
+            // retire, so the whole step behaves like one list schedule over all (TaxID, run) items.
+            // PMD chains are long and heavy-tailed (adapted step size; max ~8x the mean), null chains
+            // short and uniform: PMD first, null last fills the tail (measured chain lengths + list-
+            // schedule simulation: 21.6 % -> 2.6 % idle; profiles/r01_nuts_tuning.md).
             FitLaunch a = fl;  // PMD, all positions
             a.n_masks = 1; a.mask0 = 0; a.n_items = nc; a.work_counter = d_counters + 1;
-            if ((rc = launch_nuts_dispatch<0>(ctx, st, a, npl_for(R, 32), 32))) return rc;
             FitLaunch b = fl;  // null, all positions
             b.n_masks = 1; b.mask0 = 0; b.n_items = nc; b.work_counter = d_counters + 2;
-            if ((rc = launch_nuts_dispatch<1>(ctx, ctx->side[0], b, npl_for(R, 32), 32))) return rc;
-            if (fwd_rev) {
-                FitLaunch c = fl, d = fl;
-                c.work_counter = d_counters + 3; d.work_counter = d_counters + 4;
-                if (pack) {
-                    c.n_items = nc; d.n_items = nc; c.n_masks = 1; d.n_masks = 1; c.mask0 = 1; d.mask0 = 1;
-                    if ((rc = launch_nuts_dispatch<0>(ctx, ctx->side[1], c, 1, 16))) return rc;
-                    if ((rc = launch_nuts_dispatch<1>(ctx, ctx->side[2], d, 1, 16))) return rc;
-                } else {
-                    c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_masks = 2; d.n_masks = 2; c.mask0 = 1; d.mask0 = 1;
-                    if ((rc = launch_nuts_dispatch<0>(ctx, ctx->side[1], c, npl_for(P, 32), 32))) return rc;
-                    if ((rc = launch_nuts_dispatch<1>(ctx, ctx->side[2], d, npl_for(P, 32), 32))) return rc;
-                }
+            FitLaunch c = fl, d = fl;  // PMD / null, forward-only and reverse-only
+            c.work_counter = d_counters + 3; d.work_counter = d_counters + 4;
+            if (pack) {
+                c.n_items = nc; d.n_items = nc; c.n_masks = 1; d.n_masks = 1; c.mask0 = 1; d.mask0 = 1;
+            } else {
+                c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_masks = 2; d.n_masks = 2; c.mask0 = 1; d.mask0 = 1;
             }
+            const int npl_half = pack ? 1 : npl_for(P, 32), gw_half = pack ? 16 : 32;
+            if (fwd_rev && (rc = launch_nuts_dispatch<0>(ctx, ctx->side[1], c, npl_half, gw_half))) return rc;
+            if ((rc = launch_nuts_dispatch<0>(ctx, st, a, npl_for(R, 32), 32))) return rc;
+            if (fwd_rev && (rc = launch_nuts_dispatch<1>(ctx, ctx->side[2], d, npl_half, gw_half))) return rc;
+            if ((rc = launch_nuts_dispatch<1>(ctx, ctx->side[0], b, npl_for(R, 32), 32))) return rc;
         }
         for (int i = 0; i < 3; ++i) {
             MDG_CUDA_TRY(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));

@@ -4,6 +4,8 @@ Tolerances (BASELINE.json north_star): log-density / gradient to FP64 round-off;
 phi, D_max within 1e-5 relative; MCMC summaries within 3x Monte-Carlo standard error; the NUTS
 state machine additionally has to reproduce the oracle's chain transition by transition for the
 first transitions (both draw from the same Philox streams)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -221,6 +223,14 @@ def test_partition_and_order_invariance_bitwise(ctx):
     assert full["result"].tobytes() == unpacked["result"].tobytes()  # half-warp packing changes nothing
     other = ctx.fit_batch(tid, k, N, cfg.copy(seed=7))
     assert other["result"]["q_mean"].tobytes() != full["result"]["q_mean"].tobytes()
+    # the library's internal chunking (scratch reuse between chunks) changes nothing either
+    os.environ["MDG_FIT_CHUNK"] = "7"
+    try:
+        chunked = ctx.fit_batch(tid, k, N, cfg)
+    finally:
+        del os.environ["MDG_FIT_CHUNK"]
+    assert full["result"].tobytes() == chunked["result"].tobytes()
+    assert full["median"].tobytes() == chunked["median"].tobytes()
 
 
 @pytest.mark.parametrize("P", [25, 40])
