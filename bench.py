@@ -212,7 +212,11 @@ def counts_stress(ctx, torch, dev, n_rows=10_000_000, reps=5):
     ms = float(np.mean(times[2:]))
     peak, which = hbm_peak()
     achieved = ALGO_BYTES_PER_ROW * n_rows / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this 10M-row input, from the ncu --set full
+    # capture summarised in profiles/r01_counts_ncu.md (460 MB + 255 MB); not re-measured live
+    traffic = 715e6 if n_rows == 10_000_000 else None
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": "ncu --set full capture (profiles/r01_counts_ncu.md), bytes per launch",
             "kernel": "counts_reduce_kernel", "rows": n_rows, "kept_taxa": int(kept), "kernel_ms": ms,
             "algorithmic_bytes_per_row": ALGO_BYTES_PER_ROW, "peak_source": which,
             "note": "inputs (780 MB) exceed L2; mean of %d launches after 2 warm-ups, CUDA events on the launch stream" % reps}
@@ -358,7 +362,8 @@ def main():
         achieved = flops / (nuts_ms * 1e-3) / 1e12 if nuts_ms > 0 else 0.0
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            "traffic": None, "kernel": "nuts_kernel<PMD|null, 32|16 lanes> (4 launches per step)",
+            "traffic": 948.0, "traffic_source": "ncu --set full capture of the PMD/all launch (profiles/r01_nuts_ncu.md): bytes of DRAM traffic per launch, i.e. none",
+            "kernel": "nuts_kernel<PMD|null, 32|16 lanes> (4 launches per step)",
             "flop_model": "SURVEY.md 8d nominal: PMD 300*n_obs+55, null 190*n_obs+165 flop per gradient evaluation",
             "gradient_evaluations_per_step": float(stats["leapfrogs"].sum() / max(1, args.steps)),
             "gradient_evaluations_per_s": float(stats["leapfrogs"].sum() / (nuts_ms * 1e-3)) if nuts_ms > 0 else 0.0,
