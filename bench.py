@@ -354,6 +354,21 @@ def main():
     e2e_ms, e2e_fits = timed(step_host, args.steps)
     clocks = sampler.stop()
 
+    # ---------------- the north star's reduced unit: no forward-only / reverse-only refits ----------------
+    cfg_reduced = cfg.copy(do_fwd_rev=0)
+
+    def step_reduced(record):
+        flush.zero_()
+        n_fit = ctx.counts_reduce_device(cols, outs)
+        ctx.fit_batch_device(outs["tax_id"][:n_fit], outs["k"][:n_fit], outs["N"][:n_fit], res_dev, cfg_reduced,
+                             median=med_dev[0], hpdi_lo=med_dev[1], hpdi_hi=med_dev[2], noise3=outs["noise"][:n_fit])
+        if record:
+            stats["launches"] += 3 + ctx.timings()["n_launches"]
+        return n_fit
+
+    step_reduced(False)
+    red_ms, red_fits = timed(step_reduced, 1)
+
     # ---------------- rooflines, CPU baseline (rank 0 only) ----------------
     if rank == 0:
         fp64_peak = ctx.fp64_peak_tflops()
@@ -368,6 +383,10 @@ def main():
             "gradient_evaluations_per_step": float(stats["leapfrogs"].sum() / max(1, args.steps)),
             "gradient_evaluations_per_s": float(stats["leapfrogs"].sum() / (nuts_ms * 1e-3)) if nuts_ms > 0 else 0.0,
             "peak_source": "FP64 FMA peak measured live on this GPU (mdg_measure_fp64_peak); not in MEASURED_PEAKS.json",
+            "ncu": {"source": "profiles/r01_nuts_ncu.md (ncu --set full, PMD/all launch; static, not re-measured by this run)",
+                    "warp_instructions_per_evaluation": 1140, "fp64_instruction_share": 0.398,
+                    "fp64_pipe_busy_full_size": 0.47, "ipc_per_scheduler_full_size": 0.59,
+                    "pipe_busy_pct_in_capture": {"fp64": 32.0, "alu": 15.1, "xu_sfu": 7.1, "fma_fp32": 6.1, "lsu": 24.6, "issue_slots": 46.1}},
             "note": "HBM traffic of the fit kernels is negligible (240 B in, ~1 KB out per TaxID): compute bound, no tensor cores",
         }
         roofline_counts = None if args.no_counts_stress else counts_stress(ctx, torch, dev)
@@ -386,6 +405,9 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "roofline_counts": roofline_counts,
+            "reduced_unit": {"value": red_fits / (red_ms * 1e-3), "unit": UNIT, "ms_per_step": red_ms, "steps": 1,
+                             "what": "counts + MAP + PMD/null NUTS on all positions + WAIC + predictive D_max, WITHOUT the forward-only / "
+                                     "reverse-only refits of fits.py:298-356 (the north star's reduced unit; `value` above is the full fit)"},
             "cpu_baseline": cpu,
             "kernel_ms_per_step": {"counts": per_step("counts_ms"), "map": per_step("map_ms"), "nuts": per_step("nuts_ms"),
                                    "ppc": per_step("ppc_ms"), "assemble": per_step("assemble_ms")},
