@@ -253,6 +253,24 @@ int mdg_tsv_parse(mdg_ctx* ctx, int mem, const char* text, int64_t n_bytes, int6
                   uint32_t* counts16, int64_t counts_stride, int64_t* name_span, int64_t* rank_span,
                   int64_t* out_n_rows /* host */, int32_t* out_n_cols /* host: 20 or 22 */);
 
+/*
+ * K8 — select_top: `--max-fits` on the device. Replaces fits.extract_top_max_fits
+ * (fits.py:736-744: df_counts.groupby("tax_id")["N_alignments"].sum().nlargest(max_fits), then the
+ * rows of those TaxIDs in df_counts order) for the arrays mdg_counts_reduce produces.
+ * Per-row inputs [n_rows]: tax_id_row, n_alignments_row, keep_row (the cut flags of
+ * mdg_counts_reduce; NULL = every row counts). Per-TaxID inputs [n_tax]: tax_id, first_row (as
+ * returned by mdg_counts_reduce; rows of a TaxID are contiguous). weight(t) = sum of
+ * n_alignments_row over the kept rows of TaxID t. The min(n_top, n_tax) TaxIDs with the largest
+ * weight are selected; ties at the cut go to the smaller tax id (pandas nlargest keep="first" on
+ * the tax_id-sorted groupby index). out_index receives their positions in the per-TaxID arrays in
+ * ascending order (= df_counts order), out_weight (optional, [n_tax]) all weights, *out_n (host
+ * pointer) the number selected. tax ids must be unique (MDG_ERR_INVALID otherwise).
+ */
+int mdg_select_top(mdg_ctx* ctx, int mem, int64_t n_rows,
+                   const int64_t* tax_id_row, const uint32_t* n_alignments_row, const uint8_t* keep_row,
+                   int64_t n_tax, const int64_t* tax_id, const int64_t* first_row, int64_t n_top,
+                   uint64_t* out_weight, int64_t* out_index, int64_t* out_n /* host pointer */);
+
 /* building blocks exported for the parity tests (device evaluation of single functions) */
 
 /* evaluate lgamma and digamma of x[0..n) on the GPU with the fit kernels' own routines */

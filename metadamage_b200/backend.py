@@ -157,6 +157,34 @@ class Context:
             g("tax_id"), g("n_alignments"), g("first_row"), g("k"), g("N"), g("noise"), int(outs["k"].shape[0]), C.byref(n_tax)))
         return n_tax.value
 
+    # ------------------------------------------------------------------ K8 (N3)
+    def select_top(self, tax_id_row, n_alignments_row, keep_row, tax_id, first_row, n_top, want_weight=False):
+        """fits.extract_top_max_fits (fits.py:736-744) on the arrays counts_reduce returns: positions (in the
+        per-TaxID arrays, ascending = df_counts order) of the n_top TaxIDs with the largest sum of
+        N_alignments over their kept rows; ties at the cut go to the smaller tax id."""
+        tax_id_row = np.ascontiguousarray(tax_id_row, dtype=np.int64)
+        n_alignments_row = np.ascontiguousarray(n_alignments_row, dtype=np.uint32)
+        keep_row = None if keep_row is None else np.ascontiguousarray(keep_row, dtype=np.uint8)
+        tax_id = np.ascontiguousarray(tax_id, dtype=np.int64)
+        first_row = np.ascontiguousarray(first_row, dtype=np.int64)
+        n_tax = len(tax_id)
+        index = np.empty(max(0, min(int(n_top), n_tax)), np.int64)
+        weight = np.empty(n_tax, np.uint64) if want_weight else None
+        n_out = C.c_int64(0)
+        _lib.check(self._lib.mdg_select_top(self._h, MDG_HOST, len(tax_id_row), ptr(tax_id_row), ptr(n_alignments_row), ptr(keep_row),
+                                            n_tax, ptr(tax_id), ptr(first_row), int(n_top), ptr(weight), ptr(index), C.byref(n_out)))
+        index = index[:n_out.value]
+        return (index, weight) if want_weight else index
+
+    def select_top_device(self, cols, outs, n_tax, n_top, out_index, out_weight=None):
+        """K8 on torch CUDA tensors: `cols` / `outs` as given to / filled by counts_reduce_device;
+        out_index: int64 CUDA tensor with room for min(n_top, n_tax) entries. Returns how many were selected."""
+        n_out = C.c_int64(0)
+        _lib.check(self._lib.mdg_select_top(self._h, MDG_DEVICE, cols["tax_id"].numel(), _dptr(cols["tax_id"]), _dptr(cols["n_alignments"]),
+                                            _dptr(outs.get("keep")), int(n_tax), _dptr(outs["tax_id"]), _dptr(outs["first_row"]), int(n_top),
+                                            _dptr(out_weight), _dptr(out_index), C.byref(n_out)))
+        return n_out.value
+
     # ------------------------------------------------------------------ K3-K7
     def fit_batch(self, tax_id, k, N, cfg=None, mism12=None, noise3=None, want_samples=False,
                   want_trace=False, want_waic=False):

@@ -15,6 +15,8 @@ HEADERS = [
     os.path.join(_HERE, "csrc", "mdg_fit_kernels.cuh"),
     os.path.join(_HERE, "csrc", "mdg_post_kernels.cuh"),
     os.path.join(_HERE, "csrc", "mdg_counts_kernel.cuh"),
+    os.path.join(_HERE, "csrc", "mdg_tsv_kernel.cuh"),
+    os.path.join(_HERE, "csrc", "mdg_select_kernel.cuh"),
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

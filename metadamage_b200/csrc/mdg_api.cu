@@ -9,6 +9,7 @@
 
 #include "mdg_counts_kernel.cuh"
 #include "mdg_tsv_kernel.cuh"
+#include "mdg_select_kernel.cuh"
 #include "mdg_post_kernels.cuh"
 
 namespace mdg {
@@ -615,6 +616,111 @@ int mdg_tsv_parse(mdg_ctx* ctx, int mem, const char* text, int64_t n_bytes, int6
         return MDG_ERR_INVALID;
     }
     *out_n_rows = n_lines;
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8 (N3): --max-fits on the device
+// ---------------------------------------------------------------------------------------------
+int mdg_select_top(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_id_row, const uint32_t* n_alignments_row,
+                   const uint8_t* keep_row, int64_t n_tax, const int64_t* tax_id, const int64_t* first_row, int64_t n_top,
+                   uint64_t* out_weight, int64_t* out_index, int64_t* out_n) {
+    if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
+    if (n_rows < 0 || n_tax < 0 || n_top < 0 || !out_n || (mem != MDG_HOST && mem != MDG_DEVICE) ||
+        (n_tax > 0 && (!tax_id_row || !n_alignments_row || !tax_id || !first_row || !out_index || n_rows <= 0))) {
+        set_error("mdg_select_top: invalid argument");
+        return MDG_ERR_INVALID;
+    }
+    MDG_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->timings = mdg_timings{};
+    const long long take = std::min<long long>(n_top, n_tax);
+    *out_n = take;
+    if (n_tax == 0 || (take == 0 && !out_weight)) { *out_n = 0; return MDG_OK; }
+    const bool host = (mem == MDG_HOST);
+    const size_t nr = (size_t)n_rows, nt = (size_t)n_tax;
+    int rc;
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+    const long long* d_tax_row = reinterpret_cast<const long long*>(tax_id_row);
+    const uint32_t* d_nal_row = n_alignments_row; const uint8_t* d_keep = keep_row;
+    const long long* d_tax = reinterpret_cast<const long long*>(tax_id);
+    const long long* d_first = reinterpret_cast<const long long*>(first_row);
+    unsigned long long* d_weight = reinterpret_cast<unsigned long long*>(out_weight);
+    long long* d_index = reinterpret_cast<long long*>(out_index);
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    if (host) {
+        const size_t in_bytes = up(nr * 8) + up(nr * 4) + up(nr) + 2 * up(nt * 8);
+        if ((rc = ctx->buf[22].ensure(in_bytes))) return rc;
+        unsigned char* b = ctx->buf[22].as<unsigned char>();
+        size_t o = 0;
+        auto put = [&](const void* src, size_t bytes) -> void* {
+            void* d = b + o; o += up(bytes);
+            if (src) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+            return d;
+        };
+        d_tax_row = (const long long*)put(tax_id_row, nr * 8);
+        d_nal_row = (const uint32_t*)put(n_alignments_row, nr * 4);
+        void* kp = put(keep_row, nr);
+        d_keep = keep_row ? (const uint8_t*)kp : nullptr;
+        d_tax = (const long long*)put(tax_id, nt * 8);
+        d_first = (const long long*)put(first_row, nt * 8);
+        MDG_CUDA_TRY(cudaGetLastError());
+    }
+    const int n_blocks = (int)((n_tax + kTopThreads - 1) / kTopThreads);
+    const size_t scratch = up(kTopPasses * 256 * 4) + up((size_t)n_blocks * 4) + up((size_t)n_blocks * 8) + up(8) +
+                           ((host || !out_weight) ? up(nt * 8) : 0) + (host ? up((size_t)take * 8 + 8) : 0);
+    if ((rc = ctx->buf[23].ensure(scratch))) return rc;
+    unsigned char* sb = ctx->buf[23].as<unsigned char>();
+    size_t so = 0;
+    auto carve = [&](size_t bytes) { void* q = sb + so; so += up(bytes); return q; };
+    TopLaunch tl = {};
+    tl.n_tax = n_tax; tl.n_top = take;
+    tl.hist = (unsigned int*)carve(kTopPasses * 256 * 4);
+    tl.block_cnt = (int*)carve((size_t)n_blocks * 4);
+    tl.block_base = (long long*)carve((size_t)n_blocks * 8);
+    long long* d_total = (long long*)carve(8);
+    if (host || !out_weight) d_weight = (unsigned long long*)carve(nt * 8);
+    if (host) d_index = (long long*)carve((size_t)take * 8 + 8);
+    tl.weight = d_weight; tl.tax_id = d_tax; tl.out_index = d_index;
+    MDG_CUDA_TRY(cudaMemsetAsync(tl.hist, 0, kTopPasses * 256 * 4, st));
+    top_weight_kernel<<<(unsigned)((n_tax * 32 + kTopThreads - 1) / kTopThreads), kTopThreads, 0, st>>>(
+        n_rows, d_tax_row, d_nal_row, d_keep, n_tax, d_first, d_weight);
+    MDG_CUDA_TRY(cudaGetLastError());
+    ctx->timings.n_launches++;
+    if (take == 0) {
+        MDG_CUDA_TRY(cudaMemsetAsync(d_total, 0, 8, st));  // weights only
+    } else if (take < n_tax) {
+        const int hist_grid = std::min(n_blocks, 4 * ctx->num_sms);
+        for (int pass = 0; pass < kTopPasses; ++pass) top_hist_kernel<<<hist_grid, kTopThreads, 0, st>>>(tl, pass);
+        MDG_CUDA_TRY(cudaGetLastError());
+        top_emit_kernel<0><<<n_blocks, kTopThreads, 0, st>>>(tl);
+        counts_scan_kernel<<<1, 1024, 0, st>>>(tl.block_cnt, n_blocks, tl.block_base, d_total);
+        top_emit_kernel<1><<<n_blocks, kTopThreads, 0, st>>>(tl);
+        MDG_CUDA_TRY(cudaGetLastError());
+        ctx->timings.n_launches += kTopPasses + 3;
+    } else {
+        // everything is taken: threshold = smallest possible key (all-zero histograms replay to digit 0)
+        top_emit_kernel<0><<<n_blocks, kTopThreads, 0, st>>>(tl);
+        counts_scan_kernel<<<1, 1024, 0, st>>>(tl.block_cnt, n_blocks, tl.block_base, d_total);
+        top_emit_kernel<1><<<n_blocks, kTopThreads, 0, st>>>(tl);
+        MDG_CUDA_TRY(cudaGetLastError());
+        ctx->timings.n_launches += 3;
+    }
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[9], st));
+    if (host) {
+        if (take > 0) MDG_CUDA_TRY(cudaMemcpyAsync(out_index, d_index, (size_t)take * 8, cudaMemcpyDeviceToHost, st));
+        if (out_weight) MDG_CUDA_TRY(cudaMemcpyAsync(out_weight, d_weight, nt * 8, cudaMemcpyDeviceToHost, st));
+    }
+    long long h_total = 0;
+    MDG_CUDA_TRY(cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[9]);
+    ctx->timings.total_ms = ms;
+    if (h_total != take) {
+        set_error("mdg_select_top: selected %lld of %lld (duplicate tax ids in the per-TaxID arrays?)", h_total, take);
+        return MDG_ERR_INVALID;
+    }
     return MDG_OK;
 }
 

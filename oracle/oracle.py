@@ -140,6 +140,26 @@ def counts_reduce(tax_id, n_alignments, is_reverse, pos0, counts16, fwd="CT", re
     return out
 
 
+def select_top(tax_id_row, n_alignments_row, keep_row, tax_id, first_row, n_top):
+    """fits.py:736-744 extract_top_max_fits restated on the arrays of counts_reduce: positions (ascending) in
+    the per-TaxID arrays of the n_top TaxIDs with the largest sum of N_alignments over their kept rows; the
+    groupby result is indexed by sorted tax_id and nlargest keeps the first among ties, i.e. the smaller id.
+    Returns (index, weight)."""
+    tax_id_row = np.asarray(tax_id_row, dtype=np.int64)
+    nal = np.asarray(n_alignments_row, dtype=np.uint64)
+    keep = np.ones(len(tax_id_row), bool) if keep_row is None else np.asarray(keep_row).astype(bool)
+    tax_id = np.asarray(tax_id, dtype=np.int64)
+    first_row = np.asarray(first_row, dtype=np.int64)
+    weight = np.zeros(len(tax_id), np.uint64)
+    for t, r0 in enumerate(first_row):  # rows of a TaxID are contiguous
+        r1 = r0
+        while r1 < len(tax_id_row) and tax_id_row[r1] == tax_id_row[r0]:
+            r1 += 1
+        weight[t] = nal[r0:r1][keep[r0:r1]].sum()
+    order = sorted(range(len(tax_id)), key=lambda t: (-int(weight[t]), int(tax_id[t])))
+    return np.array(sorted(order[:max(0, int(n_top))]), dtype=np.int64), weight
+
+
 def logp_grad(k, N, u, cfg=None, model=0, lane_mask=0, with_jacobian=True, max_position=None):
     """log joint + gradient wrt unconstrained u for one TaxID; u: [n_eval][4]."""
     cfg = cfg or default_config()

@@ -17,7 +17,9 @@ pure pandas / numpy are then executed:
               matrix), compute_n_sigma, compute_assymmetry_combined_vs_forwardreverse,
               add_noise_estimates, group_to_numpyro_data              (fits.py:147-227, 359-419)
 
-Outputs: counts_golden.npz, fits_golden.npz (small; committed).
+              extract_top_max_fits / get_top_max_fits                  (fits.py:736-751)
+
+Outputs: counts_golden.npz, fits_golden.npz, topn_golden.npz (small; committed).
 """
 import importlib
 import os
@@ -233,10 +235,36 @@ def make_fits_golden(counts, fits):
     return out
 
 
+def make_topn_golden(fits):
+    """fits.extract_top_max_fits / get_top_max_fits (fits.py:736-751) on df_counts-like frames with many
+    ties in the per-TaxID sums: the selected TaxIDs in df_counts order."""
+    rng = np.random.default_rng(20240018)
+    out = {}
+    for case, (n_tax, levels) in enumerate([(200, 12), (64, 3), (1000, 40)]):
+        tax = rng.permutation(rng.choice(10 ** 6, n_tax, replace=False)).astype(np.int64)
+        nal = rng.choice(np.sort(rng.integers(10, 5000, levels)), n_tax).astype(np.uint32)
+        rows = rng.choice([30, 30, 30, 28, 16, 2], n_tax)
+        order = np.lexsort((-tax, -nal.astype(np.int64)))  # counts.sort_by_alignments: N_alignments desc, tax_id desc
+        tax, nal, rows = tax[order], nal[order], rows[order]
+        tax_row = np.repeat(tax, rows)
+        nal_row = np.repeat(nal, rows)
+        df = pd.DataFrame({"tax_id": pd.Series(tax_row).astype("category"), "N_alignments": nal_row.astype(np.uint32),
+                           "position": np.concatenate([np.arange(r) for r in rows]).astype(np.int8)})
+        out[f"case{case}_tax_id_row"] = tax_row
+        out[f"case{case}_n_alignments_row"] = nal_row
+        for n_top in (1, 5, 17, n_tax // 2, n_tax - 1, n_tax, n_tax + 7):
+            top = fits.get_top_max_fits(df, n_top)
+            out[f"case{case}_top{n_top}"] = pd.unique(top["tax_id"]).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "topn_golden.npz"), **out)
+    return out
+
+
 def main():
     counts, fits, utils = load_reference()
     c = make_counts_golden(counts)
     f = make_fits_golden(counts, fits)
+    t = make_topn_golden(fits)
+    print("topn_golden.npz:", len(t), "arrays")
     print("counts_golden.npz:", len(c), "arrays;", "fits_golden.npz:", len(f), "arrays")
     print("n_sigma", f["n_sigma"], "asymmetry", f["asymmetry"])
     print("noise", f["noise_expected"])

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import mcse_batch_means
+from conftest import mcse_batch_means, null_posterior_quadrature
 from metadamage_b200 import _lib, synthetic as syn
 from test_oracle_nuts import synthetic_taxon
 
@@ -168,6 +168,27 @@ def test_nuts_summaries_within_mcse_of_oracle(ctx, oracle):
         # n_sigma: both are noisy functions of 2 x 3000 draws; compare on the scale of the WAIC sums
         assert abs(r["run"][0]["waic"] - e["run"][0]["waic"]) < 1.5 and abs(r["run"][1]["waic"] - e["run"][1]["waic"]) < 1.5
         assert abs(r["n_sigma"] - e["n_sigma"]) < 0.35 * (1 + abs(e["n_sigma"]))
+
+
+def test_null_model_chains_match_quadrature(ctx):
+    """Ground truth without any sampler: the null model's 2-D posterior integrated on a grid with
+    scipy's beta-binomial pmf (conftest.null_posterior_quadrature). The CUDA chains (null / all
+    positions, and null / forward-only through the half-warp kernel) must agree within 4 x MCSE."""
+    cases = [(21, dict(n_lo=200, n_hi=3000)), (22, dict(n_lo=5, n_hi=60, A=0.0, c=0.05)), (23, dict(n_lo=20000, n_hi=90000, phi=3000.0))]
+    taxa = [synthetic_taxon(seed, **kw) for seed, kw in cases]
+    tid = np.arange(len(taxa), dtype=np.int64) + 7021
+    k = np.stack([t[0] for t in taxa])
+    N = np.stack([t[1] for t in taxa])
+    got = ctx.fit_batch(tid, k, N, _lib.default_config(num_warmup=500, num_samples=4000, do_map=0), want_samples=True)
+    for i in range(len(taxa)):
+        for run, sl in ((1, slice(0, 30)), (3, slice(0, 15))):  # null/all, null/forward
+            truth = null_posterior_quadrature(k[i, sl], N[i, sl])
+            smp = got["samples"][i, run]
+            q, ld = smp[:, 0], np.log(smp[:, 3] - 2.0)
+            assert abs(q.mean() - truth["mean_q"]) < 4 * mcse_batch_means(q) + 1e-12, (i, run, q.mean(), truth["mean_q"])
+            assert abs(ld.mean() - truth["mean_logdelta"]) < 4 * mcse_batch_means(ld) + 1e-12, (i, run, ld.mean(), truth["mean_logdelta"])
+            assert abs(q.var() - truth["var_q"]) < 5 * mcse_batch_means((q - q.mean()) ** 2) + 0.02 * truth["var_q"], (i, run, "var q")
+            assert abs(ld.var() - truth["var_logdelta"]) < 5 * mcse_batch_means((ld - ld.mean()) ** 2) + 0.02 * truth["var_logdelta"], (i, run)
 
 
 def test_waic_and_assembly_are_consistent(ctx):

@@ -3,7 +3,7 @@ random-walk Metropolis chain on the same unconstrained log density. Also: determ
 partition-independence property (results depend on (seed, tax_id) only)."""
 import numpy as np
 
-from conftest import mcse_batch_means
+from conftest import mcse_batch_means, null_posterior_quadrature
 
 
 def synthetic_taxon(seed, n_lo=200, n_hi=3000, A=0.25, q=0.35, c=0.02, phi=300.0):
@@ -127,3 +127,18 @@ def test_fit_result_fields_are_consistent(oracle):
     assert r["D_max_lower_hpdi"] <= r["D_max"] <= r["D_max_upper_hpdi"]
     # predictive median at z = 1 is a multiple of 1/N(z=1) or a half step
     assert abs(r["D_max"] * N[0] * 2 - round(r["D_max"] * N[0] * 2)) < 1e-6
+
+
+def test_null_model_nuts_matches_quadrature(oracle):
+    """No sampler on the other side: the null model's 2-D posterior integrated on a grid with scipy's
+    beta-binomial pmf. Pins the restated NUTS (and its log density, bijections and Jacobians) to
+    ground truth within 4 x MCSE."""
+    for seed, kw in ((21, dict(n_lo=200, n_hi=3000)), (22, dict(n_lo=5, n_hi=60, A=0.0, c=0.05)), (23, dict(n_lo=20000, n_hi=90000, phi=3000.0))):
+        k, N = synthetic_taxon(seed, **kw)
+        truth = null_posterior_quadrature(k, N)
+        nuts = oracle.nuts_run(k, N, tax_id=7000 + seed, run_kind=1, cfg=oracle.default_config(num_warmup=500, num_samples=4000))
+        q, ld = nuts["samples"][:, 0], np.log(nuts["samples"][:, 3] - 2.0)
+        assert abs(q.mean() - truth["mean_q"]) < 4 * mcse_batch_means(q) + 1e-12, (seed, q.mean(), truth["mean_q"])
+        assert abs(ld.mean() - truth["mean_logdelta"]) < 4 * mcse_batch_means(ld) + 1e-12, (seed, ld.mean(), truth["mean_logdelta"])
+        assert abs(q.var() - truth["var_q"]) < 5 * mcse_batch_means((q - q.mean()) ** 2) + 0.02 * truth["var_q"], (seed, "var q")
+        assert abs(ld.var() - truth["var_logdelta"]) < 5 * mcse_batch_means((ld - ld.mean()) ** 2) + 0.02 * truth["var_logdelta"], (seed, "var log delta")
