@@ -19,7 +19,10 @@ pure pandas / numpy are then executed:
 
               extract_top_max_fits / get_top_max_fits                  (fits.py:736-751)
 
-Outputs: counts_golden.npz, fits_golden.npz, topn_golden.npz (small; committed).
+  dashboard/fit_results.py : FitResults' pandas half (derived columns, ranges, marker sizes, filter,
+              single-TaxID fetches; lines 74-239), loaded stand-alone without Dash / Plotly
+
+Outputs: counts_golden.npz, fits_golden.npz, topn_golden.npz, lookups_golden.npz (small; committed).
 """
 import importlib
 import os
@@ -259,12 +262,152 @@ def make_topn_golden(fits):
     return out
 
 
+def load_reference_fit_results():
+    """dashboard/fit_results.py as a stand-alone module: the dashboard package itself needs Dash, Plotly,
+    ete3, ...; only FitResults' pandas half is executed, with dashboard.utils loaded from its file."""
+    import importlib.util
+
+    class Ctx(_Anything):
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    for name in ["about_time", "dill", "plotly.express", "plotly.graph_objects", "plotly.io", "PIL"]:
+        _stub(name)
+    sys.modules["about_time"].about_time = lambda *a, **k: Ctx()
+    d3 = ["#1F77B4", "#FF7F0E", "#2CA02C", "#D62728", "#9467BD", "#8C564B", "#E377C2", "#7F7F7F", "#BCBD22", "#17BECF"]
+    sys.modules["plotly.express"].colors = types.SimpleNamespace(qualitative=types.SimpleNamespace(D3=d3))  # _set_cmap
+    sys.modules["plotly"].express = sys.modules["plotly.express"]  # `import plotly.express as px` goes through the parent
+    import joblib
+
+    class _NoMemory:  # joblib.Memory would write ./memoization
+        def __init__(self, *a, **k):
+            pass
+
+        def cache(self, f):
+            return f
+
+    real_memory, joblib.Memory = joblib.Memory, _NoMemory
+
+    def from_file(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    dash_pkg = types.ModuleType("metadamage.dashboard")
+    dash_pkg.__path__ = []
+    sys.modules["metadamage.dashboard"] = dash_pkg
+    importlib.import_module("metadamage").dashboard = dash_pkg
+    dash_pkg.utils = from_file("metadamage.dashboard.utils", os.path.join(REF, "metadamage", "dashboard", "utils.py"))
+    mod = from_file("metadamage.dashboard.fit_results", os.path.join(REF, "metadamage", "dashboard", "fit_results.py"))
+    joblib.Memory = real_memory
+    return mod
+
+
+def make_lookups_golden(fit_results_mod):
+    """The reference's FitResults (dashboard/fit_results.py:74-239) on result files written with the
+    reference's column schema: derived columns, ranges, marker sizes, filters, single-TaxID fetches."""
+    import shutil
+    import tempfile
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from metadamage_b200 import fits as our_fits, io as our_io  # the writers under test
+    rng = np.random.default_rng(20240019)
+    folder = tempfile.mkdtemp(prefix="mdg_lookups_")
+    out = {}
+    try:
+        frames, preds = [], []
+        for shortname, n in (("sampleA", 40), ("sampleB", 25)):
+            tax = rng.choice(10 ** 5, n, replace=False).astype(np.int64)
+            df = pd.DataFrame({c: rng.normal(1.0, 1.0, n).astype(np.float32) for c in our_fits.FIT_RESULT_COLUMNS})
+            df["tax_id"] = tax
+            df["tax_name"] = [f"name{t % 7}" for t in tax]
+            df["tax_rank"] = [("species", "genus", "family")[t % 3] for t in tax]
+            for c in ("N_alignments", "N_z1_forward", "N_z1_reverse", "N_sum_forward", "N_sum_reverse", "N_sum_total",
+                      "y_sum_forward", "y_sum_reverse", "y_sum_total"):
+                df[c] = rng.integers(0 if c == "N_sum_total" else 1, 10 ** 6, n).astype(np.uint32)
+            df.loc[0, "N_sum_total"] = 0  # log10 -> -inf, must be ignored by the ranges
+            df.loc[1, "n_sigma"] = np.nan
+            df["shortname"] = shortname
+            for c in ("tax_id", "tax_name", "tax_rank", "shortname"):
+                df[c] = df[c].astype("category")
+            our_io.Parquet(os.path.join(folder, "fit_results", f"{shortname}.parquet")).save(df, metadata={"shortname": shortname})
+            pr = pd.DataFrame({"tax_id": np.repeat(tax, 30), "position": np.tile(np.r_[1:16, -1:-16:-1], n).astype(np.int8),
+                               "median": rng.random(30 * n).astype(np.float32), "hdpi_lower": rng.random(30 * n).astype(np.float32),
+                               "hdpi_upper": rng.random(30 * n).astype(np.float32)})
+            pr["shortname"] = shortname
+            for c in ("tax_id", "shortname"):
+                pr[c] = pr[c].astype("category")
+            our_io.Parquet(os.path.join(folder, "fit_predictions", f"{shortname}.parquet")).save(pr, metadata={"shortname": shortname})
+            cn = pd.DataFrame({"tax_id": np.repeat(tax, 30), "position": np.tile(np.r_[1:16, -1:-16:-1], n).astype(np.int8),
+                               "N_alignments": np.repeat(df["N_alignments"].to_numpy(), 30)})
+            cn["tax_id"] = cn["tax_id"].astype("category")
+            our_io.Parquet(os.path.join(folder, "counts", f"{shortname}.parquet")).save(cn, metadata={"shortname": shortname})
+            frames.append(df)
+        cwd = os.getcwd()
+        os.chdir("/tmp")
+        try:
+            fr = fit_results_mod.FitResults(folder)
+        finally:
+            os.chdir(cwd)
+        d = fr.df_fit_results
+        out["folder_tables"] = np.array(["fit_results", "fit_predictions", "counts"])
+        for c in ("N_alignments_log10", "N_alignments_sqrt", "N_sum_total_log10", "size"):
+            out[f"col_{c}"] = d[c].to_numpy(np.float64).copy()
+        out["tax_id_order"] = d["tax_id"].to_numpy(np.int64)
+        out["range_keys"] = np.array(sorted(fr.ranges))
+        out["range_values"] = np.array([fr.ranges[k] for k in sorted(fr.ranges)], dtype=np.float64)
+        out["max_of_size"] = np.float64(fr.max_of_size)
+        for tr in ("identity", "log10", "constant"):
+            fr.set_marker_size(tr, 12)
+            out[f"size_{tr}"] = fr.df_fit_results["size"].to_numpy(np.float64).copy()  # (to_numpy is a view; the next call overwrites it)
+            out[f"max_of_size_{tr}"] = np.float64(fr.max_of_size)
+        fr.set_marker_size("sqrt")
+        some = [int(t) for t in d["tax_id"].to_numpy()[[3, 9, 44]]]
+        filters = [
+            {"shortnames": ["sampleA"], "n_sigma": (0.0, 2.5)},
+            {"shortname": "sampleB", "N_alignments": (2.0, 5.5), "D_max": (-1.0, 3.0)},
+            {"tax_ids": some},
+            {"tax_id": some[0], "y_sum_total": (-1.0, 7.0)},
+            {"tax_ranks": ["species", "genus"], "tax_names": ["name1", "name2", "name3"], "q_mean": None},
+            {"tax_rank": "'family'", "N_sum_total": (0.0, 6.0)},
+        ]
+        out["n_filters"] = np.int64(len(filters))
+        import json
+        out["filters_json"] = np.array(json.dumps(filters))
+        for i, f in enumerate(filters):
+            out[f"filter{i}_index"] = fr.filter(f).index.to_numpy(np.int64)
+        out["single_pred_tax"] = np.int64(some[1])
+        out["single_pred_median"] = fr.get_single_fit_prediction("sampleA", some[1])["median"].to_numpy(np.float64)
+        out["single_count_rows"] = np.int64(len(fr.get_single_count_group("sampleA", some[1])))
+        # the files themselves travel with the fixture (tiny)
+        import io as _io
+        import zipfile
+        buf = _io.BytesIO()
+        with zipfile.ZipFile(buf, "w", zipfile.ZIP_DEFLATED) as z:
+            for root, _, files in os.walk(folder):
+                for fn in files:
+                    full = os.path.join(root, fn)
+                    z.write(full, os.path.relpath(full, folder))
+        out["files_zip"] = np.frombuffer(buf.getvalue(), dtype=np.uint8)
+    finally:
+        shutil.rmtree(folder, ignore_errors=True)
+    np.savez_compressed(os.path.join(HERE, "lookups_golden.npz"), **out)
+    return out
+
+
 def main():
     counts, fits, utils = load_reference()
     c = make_counts_golden(counts)
     f = make_fits_golden(counts, fits)
     t = make_topn_golden(fits)
     print("topn_golden.npz:", len(t), "arrays")
+    lk = make_lookups_golden(load_reference_fit_results())
+    print("lookups_golden.npz:", len(lk), "arrays")
     print("counts_golden.npz:", len(c), "arrays;", "fits_golden.npz:", len(f), "arrays")
     print("n_sigma", f["n_sigma"], "asymmetry", f["asymmetry"])
     print("noise", f["noise_expected"])
