@@ -344,6 +344,7 @@ def main():
         t2 = ctx.timings()
         if record:
             stats["launches"] += t1["n_launches"] + t2["n_launches"]
+            stats["chain_leapfrogs"] = out["result"]["run"]["n_leapfrog"]
             n_fit = r["n_tax"]
             e2e_bytes["h2d"] = sum(h[key].nbytes for key in h) + n_fit * (8 + 2 * R * 4 + 24)
             e2e_bytes["d2h"] = (n_rows * (4 + 4 + 4 + 4 + 1 + 8 + 1) + n_fit * (8 + 4 + 8 + 2 * R * 4 + 24)
@@ -368,6 +369,19 @@ def main():
 
     step_reduced(False)
     red_ms, red_fits = timed(step_reduced, 1)
+
+    # ---------------- longest chain (the tail of a step is one sequential Markov chain) ----------------
+    chains = stats["chain_leapfrogs"].astype(np.float64)
+    chain_max = torch.tensor([chains.max()], dtype=torch.float64, device=dev)
+    chain_sum = torch.tensor([chains.sum(), float(chains.size)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(chain_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(chain_sum, op=dist.ReduceOp.SUM)
+    chain_stats = {"mean_leapfrogs_per_chain": float(chain_sum[0].item() / chain_sum[1].item()),
+                   "max_leapfrogs_of_one_chain": float(chain_max.item()),
+                   "note": "a step cannot end before its longest chain does: a chain is sequential (one warp, ~1.5 us per leapfrog when it "
+                           "runs alone, ~4.5 us while the GPU is full); about one chain in 60 000 adapts to a collapsed step size and runs "
+                           "10-40x the mean (DESIGN.md section 7)"}
 
     # ---------------- rooflines, CPU baseline (rank 0 only) ----------------
     if rank == 0:
@@ -405,6 +419,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "roofline_counts": roofline_counts,
+            "chains": chain_stats,
             "reduced_unit": {"value": red_fits / (red_ms * 1e-3), "unit": UNIT, "ms_per_step": red_ms, "steps": 1,
                              "what": "counts + MAP + PMD/null NUTS on all positions + WAIC + predictive D_max, WITHOUT the forward-only / "
                                      "reverse-only refits of fits.py:298-356 (the north star's reduced unit; `value` above is the full fit)"},
