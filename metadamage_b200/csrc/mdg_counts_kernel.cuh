@@ -29,7 +29,7 @@ namespace mdg {
 constexpr int kCountsThreads = 128;
 constexpr int kCountsWarps = kCountsThreads / 32;
 // shared bytes per staged row, without the count columns (4 bytes per staged column on top)
-constexpr int kCountsBytesPerRow = 8 + 4 + 1 + 1 + 8 + 4 + 1 + 1 + 4 + 8 + 1;
+constexpr int kCountsBytesPerRow = 8 + 4 + 1 + 1 + 8 + 4 + 1 + 1 + 4 + 8 + 1 + 1;
 
 enum CountsError : int { CE_NONE = 0, CE_SEGMENT_TOO_LONG = 1, CE_OVERFLOW = 2, CE_CAPACITY = 3 };
 
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kCountsThreads, MDG_COUNTS_MINBLOCKS) counts_r
     int8_t* o_z = reinterpret_cast<int8_t*>(s_pos + cap);
     uint8_t* o_head = reinterpret_cast<uint8_t*>(o_z + cap);
     uint8_t* s_kept = o_head + cap;
-    uint32_t* s_dense = reinterpret_cast<uint32_t*>(s_kept + cap);  // [warps][2][2P]
+    int* s_gseg = reinterpret_cast<int*>(s_kept + cap);              // [cap / 4] segment of each 4-row group's first row
+    uint32_t* s_dense = reinterpret_cast<uint32_t*>(s_gseg + cap / 4);  // [warps][2][2P]
     __shared__ uint64_t s_bar;
     __shared__ int s_warp_cnt[kCountsWarps];
     __shared__ int s_nseg, s_nowned, s_kept_total;
@@ -290,6 +291,8 @@ __global__ void __launch_bounds__(kCountsThreads, MDG_COUNTS_MINBLOCKS) counts_r
         int off = seg_base + incl - nheads, total = 0;
 #pragma unroll
         for (int w = 0; w < kCountsWarps; ++w) { const int c = s_warp_cnt[w]; off += (w < warp) ? c : 0; total += c; }
+        // segment (index into s_seg) that this group's first row belongs to; -1 = a TaxID of the previous tile
+        if (g < ngroups) s_gseg[g] = off - ((headbits & 1u) ? 0 : 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if ((headbits >> (8 * j)) & 1u) s_seg[off++] = i0 + j;
@@ -355,11 +358,9 @@ __global__ void __launch_bounds__(kCountsThreads, MDG_COUNTS_MINBLOCKS) counts_r
         const int a0 = s_seg[0], a1 = s_seg[nowned];
         for (int g = tid + (a0 >> 2); g < ((a1 + 3) >> 2); g += kCountsThreads) {
             const int i0 = g << 2;
-            // TaxID of the first owned row of this group: binary search in the sorted head list
+            // TaxID of the first owned row of this group (recorded by the head compaction of phase 1)
             const int ifirst = i0 < a0 ? a0 : i0;
-            int lo = 0, hi = nowned - 1;
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_seg[mid] <= ifirst) lo = mid; else hi = mid - 1; }
-            int s = lo;
+            int s = i0 < a0 ? 0 : s_gseg[g];
             const uint32_t headbits = *reinterpret_cast<const uint32_t*>(o_head + i0);
             const uint32_t zpack = *reinterpret_cast<const uint32_t*>(o_z + i0);
             const uint4 nal4 = *reinterpret_cast<const uint4*>(s_nal + i0);
