@@ -30,25 +30,29 @@ struct Stream {
     }
 };
 
-// log of a Gamma(a, 1) variate: Marsaglia-Tsang with the a < 1 boost, in log space for tiny a
+// log of a Gamma(a, 1) variate: Marsaglia-Tsang with the a < 1 boost, in log space for tiny a.
+// Logs of positive normal doubles go through the table-driven log_pos, divisions through the Newton
+// reciprocal (the CUDA library versions cost 2-3x as many instructions; this kernel draws 3.2e8
+// beta-binomial variates per 10 000 TaxIDs).
 __device__ __forceinline__ double log_gamma_variate(Stream& st, double a) {
     double boost = 0.0;
-    if (a < 1.0) { boost = log(st.uniform()) / a; a += 1.0; }
-    const double dd = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+    if (a < 1.0) { boost = log_pos(st.uniform()) * rcp_pos(a); a += 1.0; }
+    const double dd = a - 1.0 / 3.0, cc = rsqrt(9.0 * dd);
     for (int guard = 0; guard < 1000; ++guard) {
         double x = st.normal();
         double v = 1.0 + cc * x;
         if (v <= 0.0) continue;
         v = v * v * v;
         double u = st.uniform();
-        if (log(u) < 0.5 * x * x + dd - dd * v + dd * log(v)) return log(dd * v) + boost;
+        const double ldv = log_pos(dd * v);  // = log(dd) + log(v)
+        if (log_pos(u) < 0.5 * x * x + dd - dd * v + dd * (ldv - log_pos(dd))) return ldv + boost;
     }
-    return log(dd) + boost;
+    return log_pos(dd) + boost;
 }
 
 __device__ __forceinline__ double beta_variate(Stream& st, double a, double b) {
     double la = log_gamma_variate(st, a), lb = log_gamma_variate(st, b);
-    return 1.0 / (1.0 + exp(lb - la));
+    return rcp_pos(1.0 + exp_fast(lb - la));
 }
 
 // Binomial(n, p): BINV inversion for n*min(p,1-p) < 10, BTRS (Hormann 1993) otherwise
@@ -59,8 +63,8 @@ __device__ __forceinline__ double binomial_variate(Stream& st, double n, double 
     if (flip) p = 1.0 - p;
     double res = 0.0;
     if (n * p < 10.0) {
-        const double q = 1.0 - p, s = p / q, a = (n + 1.0) * s;
-        const double r0 = exp(n * log1p(-p));
+        const double q = 1.0 - p, s = p * rcp_pos(q), a = (n + 1.0) * s;
+        const double r0 = exp_fast(n * log1p(-p));
         for (int guard = 0; guard < 64; ++guard) {
             double r = r0, u = st.uniform(), x = 0.0;
             bool bad = false;
@@ -68,7 +72,7 @@ __device__ __forceinline__ double binomial_variate(Stream& st, double n, double 
                 u -= r;
                 x += 1.0;
                 if (x > n || x > 2000.0) { bad = true; break; }
-                r *= (a / x - s);
+                r *= fma(a, rcp_pos(x), -s);
             }
             if (!bad) { res = x; break; }
         }
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(WARPS * 32) ppc_kernel(const PpcLaunch p) {
             uint32_t y = 0xFFFFFFFFu;
             if (s < S) {
                 const double q = smp[(size_t)s * 4], A = smp[(size_t)s * 4 + 1], c = smp[(size_t)s * 4 + 2], phi = smp[(size_t)s * 4 + 3];
-                double Dz = fma(A, exp(x * log1p(-q)), c);
+                double Dz = fma(A, exp_fast(x * log1p(-q)), c);
                 Dz = fmin(fmax(Dz, 0.0), 1.0);
                 Stream st;
                 st.key = key; st.c0 = 0u; st.c1 = (uint32_t)s; st.c2 = c2word(run_kind, P_PPC); st.c3 = (uint32_t)dense; st.have = false; st.stash = 0.0;
