@@ -335,10 +335,23 @@ def main():
     h = {key: pinned(g[key]) for key in ("tax_id", "n_alignments", "is_reverse", "pos0", "counts16")}
     e2e_bytes = {"h2d": 0, "d2h": 0}
 
+    def pinned_empty(shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        return t.numpy()[:nbytes].view(dtype).reshape(shape)
+
+    # result buffers of the host API, pinned and reused from step to step (Context.counts_reduce(out=...))
+    host_out = dict(
+        n_fwd_ref=pinned_empty(n_rows, np.uint32), n_rev_ref=pinned_empty(n_rows, np.uint32), f_fwd=pinned_empty(n_rows, np.float32),
+        f_rev=pinned_empty(n_rows, np.float32), z=pinned_empty(n_rows, np.int8), y_sum_total=pinned_empty(n_rows, np.uint64),
+        keep=pinned_empty(n_rows, np.uint8), tax_id=pinned_empty(n_in_tax, np.int64), n_alignments=pinned_empty(n_in_tax, np.uint32),
+        first_row=pinned_empty(n_in_tax, np.int64), k=pinned_empty((n_in_tax, R), np.uint32), N=pinned_empty((n_in_tax, R), np.uint32),
+        noise=pinned_empty((n_in_tax, 3), np.float64))
+
     def step_host(record):
         flush.zero_()
         r = ctx.counts_reduce(h["tax_id"], h["n_alignments"], h["is_reverse"], h["pos0"], h["counts16"],
-                              max_position=P, want_noise=True)
+                              max_position=P, want_noise=True, out=host_out)
         t1 = ctx.timings()
         out = ctx.fit_batch(r["tax_id"], r["k"], r["N"], cfg, noise3=r["noise"])
         t2 = ctx.timings()

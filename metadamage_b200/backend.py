@@ -97,8 +97,10 @@ class Context:
 
     # ------------------------------------------------------------------ K1
     def counts_reduce(self, tax_id, n_alignments, is_reverse, pos0, counts16, fwd="CT", rev="GA",
-                      max_position=15, min_alignments=10, min_y_sum=10, want_noise=False, want_rows=True):
-        """counts.py:237-256 on host SoA columns (numpy). Returns a dict of numpy arrays."""
+                      max_position=15, min_alignments=10, min_y_sum=10, want_noise=False, want_rows=True, out=None):
+        """counts.py:237-256 on host SoA columns (numpy). Returns a dict of numpy arrays.
+        `out` (optional): a dict from an earlier call with the same shapes (or caller-allocated, e.g.
+        pinned, arrays under the same keys); its buffers are reused instead of allocating new ones."""
         n = len(tax_id)
         P = int(max_position)
         tax_id = np.ascontiguousarray(tax_id, dtype=np.int64)
@@ -112,18 +114,28 @@ class Context:
         rr, ro = _base_index(rev)
         # room for every run of equal tax_id (an upper bound of the kept TaxIDs)
         m_cap = int(np.count_nonzero(tax_id[1:] != tax_id[:-1])) + 1 if n else 0
+        reuse = out if out is not None else {}
+
+        def buf(key, shape, dtype):
+            a = reuse.get("_buf_" + key, reuse.get(key))
+            shape = shape if isinstance(shape, tuple) else (shape,)
+            if a is not None and a.dtype == np.dtype(dtype) and a.shape[1:] == shape[1:] and a.shape[0] >= shape[0] and a.flags["C_CONTIGUOUS"]:
+                return a
+            return np.empty(shape, dtype)
+
         out = {}
         if want_rows:
             out.update(
-                n_fwd_ref=np.empty(n, np.uint32), n_rev_ref=np.empty(n, np.uint32),
-                f_fwd=np.empty(n, np.float32), f_rev=np.empty(n, np.float32),
-                z=np.empty(n, np.int8), y_sum_total=np.empty(n, np.uint64), keep=np.empty(n, np.uint8),
+                n_fwd_ref=buf("n_fwd_ref", n, np.uint32), n_rev_ref=buf("n_rev_ref", n, np.uint32),
+                f_fwd=buf("f_fwd", n, np.float32), f_rev=buf("f_rev", n, np.float32),
+                z=buf("z", n, np.int8), y_sum_total=buf("y_sum_total", n, np.uint64), keep=buf("keep", n, np.uint8),
             )
         out.update(
-            tax_id=np.empty(m_cap, np.int64), n_alignments=np.empty(m_cap, np.uint32), first_row=np.empty(m_cap, np.int64),
-            k=np.empty((m_cap, 2 * P), np.uint32), N=np.empty((m_cap, 2 * P), np.uint32),
-            noise=np.empty((m_cap, 3), np.float64) if want_noise else None,
+            tax_id=buf("tax_id", m_cap, np.int64), n_alignments=buf("n_alignments", m_cap, np.uint32), first_row=buf("first_row", m_cap, np.int64),
+            k=buf("k", (m_cap, 2 * P), np.uint32), N=buf("N", (m_cap, 2 * P), np.uint32),
+            noise=buf("noise", (m_cap, 3), np.float64) if want_noise else None,
         )
+        full = {"_buf_" + key: val for key, val in out.items() if val is not None}  # full-capacity buffers, for the next call
         n_tax = C.c_int64(0)
         g = out.get
         _lib.check(self._lib.mdg_counts_reduce(
@@ -136,7 +148,12 @@ class Context:
         for key in ("tax_id", "n_alignments", "first_row", "k", "N", "noise"):
             if out[key] is not None:
                 out[key] = out[key][:m]
+        if want_rows:
+            for key in ("n_fwd_ref", "n_rev_ref", "f_fwd", "f_rev", "z", "y_sum_total", "keep"):
+                out[key] = out[key][:n]
         out["n_tax"] = m
+        if reuse:
+            out.update(full)
         return out
 
     def counts_reduce_device(self, cols, outs, fwd="CT", rev="GA", max_position=15, min_alignments=10,

@@ -38,6 +38,24 @@ def test_counts_match_oracle_on_samples(ctx, oracle, sample_inputs, name):
     assert_same(r, o)
 
 
+def test_counts_output_buffers_can_be_reused(ctx, oracle):
+    """Context.counts_reduce(out=...) writes into the arrays of an earlier result (or caller-allocated,
+    e.g. pinned, ones) instead of allocating: same values, same memory."""
+    g = syn.make_mismatch_matrix(800, seed=12)
+    args = (g["tax_id"], g["n_alignments"], g["is_reverse"], g["pos0"], g["counts16"])
+    first = ctx.counts_reduce(*args, want_noise=True)
+    snapshot = {key: np.array(val, copy=True) for key, val in first.items() if isinstance(val, np.ndarray)}
+    second = ctx.counts_reduce(*args, want_noise=True, out=first)
+    third = ctx.counts_reduce(*args, want_noise=True, out=second)
+    for key, val in snapshot.items():
+        assert np.array_equal(third[key], val, equal_nan=True), key
+    assert np.shares_memory(third["n_fwd_ref"], first["n_fwd_ref"]) and np.shares_memory(third["k"], second["k"])
+    assert_same({k_: v for k_, v in third.items() if not k_.startswith("_buf_")}, oracle.counts_reduce(*args))
+    # buffers of the wrong shape are simply not used
+    other = ctx.counts_reduce(*args, max_position=7, out=third)
+    assert other["k"].shape[1] == 14 and not np.shares_memory(other["k"], third["k"])
+
+
 @pytest.mark.parametrize("P,seed,fwd,rev", [(15, 1, "CT", "GA"), (25, 2, "GA", "CT"), (7, 3, "CT", "GA"), (40, 4, "AG", "TC")])
 def test_counts_match_oracle_on_synthetic(ctx, oracle, P, seed, fwd, rev):
     g = syn.make_mismatch_matrix(3000, max_position=P, seed=seed, fwd=fwd, rev=rev)
