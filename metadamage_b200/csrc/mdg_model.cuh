@@ -151,6 +151,7 @@ __device__ __forceinline__ void eval_model(const LaneObs<NPL>& ob, const double 
     }
     // position-independent pieces: the spare slot (k = N = 0) has just evaluated them
     double lgphi, dgphi;
+    has_spare = (GW == 32) ? (__all_sync(0xffffffffu, has_spare) != 0) : has_spare;  // provably uniform: plain branches
     if (has_spare) {
         lgphi = __shfl_sync(gmask, lg3[NPL - 1], GW - 1, GW);
         dgphi = __shfl_sync(gmask, dg3[NPL - 1], GW - 1, GW);
