@@ -411,11 +411,11 @@ def main():
             "gradient_evaluations_per_s": float(stats["leapfrogs"].sum() / (nuts_ms * 1e-3)) if nuts_ms > 0 else 0.0,
             "peak_source": "FP64 FMA peak measured live on this GPU (mdg_measure_fp64_peak); not in MEASURED_PEAKS.json",
             "ncu": {"source": "profiles/r01_nuts_ncu.md (ncu --set full, PMD/all launch; static, not re-measured by this run)",
-                    "warp_instructions_per_evaluation": 1140, "fp64_instruction_share": 0.398,
-                    "executed_fp64_flop_per_evaluation": 21800,
-                    "executed_fp64_tflops_at_this_rate": 21800 * float(stats["leapfrogs"].sum() / (nuts_ms * 1e-3)) / 1e12 if nuts_ms > 0 else 0.0,
-                    "fp64_pipe_busy_full_size": 0.47, "ipc_per_scheduler_full_size": 0.59,
-                    "pipe_busy_pct_in_capture": {"fp64": 32.0, "alu": 15.1, "xu_sfu": 7.1, "fma_fp32": 6.1, "lsu": 24.6, "issue_slots": 46.1}},
+                    "warp_instructions_per_evaluation": 1096, "fp64_instruction_share": 0.414,
+                    "executed_fp64_flop_per_evaluation": 20850,
+                    "executed_fp64_tflops_at_this_rate": 20850 * float(stats["leapfrogs"].sum() / (nuts_ms * 1e-3)) / 1e12 if nuts_ms > 0 else 0.0,
+                    "fp64_pipe_busy_full_size": 0.48, "ipc_per_scheduler_full_size": 0.58,
+                    "pipe_busy_pct_in_capture": {"fp64": 33.3, "alu": 14.8, "xu_sfu": 7.4, "fma_fp32": 5.5, "lsu": 25.5, "issue_slots": 46.5}},
             "note": "HBM traffic of the fit kernels is negligible (240 B in, ~1 KB out per TaxID): compute bound, no tensor cores",
         }
         roofline_counts = None if args.no_counts_stress else counts_stress(ctx, torch, dev)
