@@ -136,14 +136,23 @@ constexpr int kNutsWarps = 4;
 constexpr int kMapWarps = 4;
 constexpr int kPpcWarps = 4;
 
-template <int MODEL, int NPL, int GW>
-int launch_nuts(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl) {
-    auto kern = nuts_kernel<MODEL, NPL, GW, kNutsWarps>;
+template <int MODEL, int NPL, int GW, bool SPARE>
+int launch_nuts_spare(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl) {
+    auto kern = nuts_kernel<MODEL, NPL, GW, kNutsWarps, SPARE>;
     int grid = persistent_grid(kern, kNutsWarps * 32, 0, ctx->num_sms, fl.n_items, kNutsWarps);
     kern<<<grid, kNutsWarps * 32, 0, st>>>(fl);
     MDG_CUDA_TRY(cudaGetLastError());
     ctx->timings.n_launches++;
     return MDG_OK;
+}
+
+template <int MODEL, int NPL, int GW>
+int launch_nuts(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl) {
+    // does every run of this launch leave the last slot of its lane group free?
+    bool spare = true;
+    if (GW == 16) spare = fl.P < NPL * GW;  // halves run masks 1 and 2: P positions each
+    else for (int m = fl.mask0; m < fl.mask0 + fl.n_masks; ++m) spare = spare && ((m == 0 ? 2 * fl.P : fl.P) < NPL * GW);
+    return spare ? launch_nuts_spare<MODEL, NPL, GW, true>(ctx, st, fl) : launch_nuts_spare<MODEL, NPL, GW, false>(ctx, st, fl);
 }
 
 template <int MODEL>

@@ -142,7 +142,10 @@ __device__ __forceinline__ void draw_momentum(uint2 key, uint32_t c1, uint32_t c
 #ifndef MDG_NUTS_MINBLOCKS
 #define MDG_NUTS_MINBLOCKS 4
 #endif
-template <int MODEL, int NPL, int GW, int WARPS>
+// SPARE: every run of the launch leaves the group's last slot without a position (n_obs < NPL * GW), so the
+// position-independent lgamma/digamma values come from that slot (eval_model). A template parameter:
+// the fallback (three more inlined evaluations) then does not exist in the hot loop's code at all.
+template <int MODEL, int NPL, int GW, int WARPS, bool SPARE>
 __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(const FitLaunch p) {
     constexpr int D = ModelDim<MODEL>::value;
     constexpr int GROUPS = 32 / GW;
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
         if (GW == 32) { tax = (int)(item / (unsigned)p.n_masks); mask = p.mask0 + (int)(item % (unsigned)p.n_masks); }
         else { tax = (int)item; mask = 1 + grp; }
         const int run_kind = mask * 2 + MODEL;
-        const bool has_spare = (mask == 0 ? 2 * P : P) < NPL * GW;
+        const bool has_spare = SPARE;  // the host checked (mask == 0 ? 2 * P : P) < NPL * GW for every mask of the launch
         const uint2 key = make_key(p.cfg.seed, p.tax_id[tax]);
 
         LaneObs<NPL> ob;
