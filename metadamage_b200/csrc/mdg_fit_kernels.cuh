@@ -820,8 +820,11 @@ __device__ void map_fit_group(const LaneObs<NPL>& ob, const double (&logC)[NPL],
     out.converged = converged ? 1u : 0u;
 }
 
+#ifndef MDG_MAP_MINBLOCKS
+#define MDG_MAP_MINBLOCKS 4
+#endif
 template <int NPL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) map_kernel(const MapLaunch p) {
+__global__ void __launch_bounds__(WARPS * 32, MDG_MAP_MINBLOCKS) map_kernel(const MapLaunch p) {
     __shared__ unsigned int sh_item[WARPS];
     __shared__ double2 sh_prior[2][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
