@@ -20,5 +20,5 @@ ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
 r = bench.counts_stress(ctx, torch, dev, reps=int(os.environ.get("MDG_COUNTS_REPS", "1")))
 print("counts", r["kernel_ms"], "ms", r["achieved"], "GB/s")
 tid, k, N, g = syn.dense_fit_batch(n_fit)
-out = ctx.fit_batch(tid, k, N, _lib.default_config(num_warmup=warm, num_samples=samp))
+out = ctx.fit_batch(tid, k, N, _lib.default_config(num_warmup=warm, num_samples=samp, do_fwd_rev=int(os.environ.get("MDG_PT_FWD_REV", "1"))))
 print("fit", ctx.timings())
