@@ -176,7 +176,7 @@ def run_reference(args):
         "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def counts_stress(ctx, torch, dev, n_rows=10_000_000, reps=5):
@@ -442,12 +442,22 @@ def main():
             "kernel_ms_per_step": {"counts": per_step("counts_ms"), "map": per_step("map_ms"), "nuts": per_step("nuts_ms"),
                                    "ppc": per_step("ppc_ms"), "assemble": per_step("assemble_ms")},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """stdout carries ONE JSON line: library chatter written to file descriptor 1 (NCCL prints its version
+    there under torchrun) is sent to stderr; print() keeps the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 if __name__ == "__main__":
+    _json_only_stdout()
     main()
