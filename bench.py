@@ -392,9 +392,10 @@ def main():
         dist.all_reduce(chain_sum, op=dist.ReduceOp.SUM)
     chain_stats = {"mean_leapfrogs_per_chain": float(chain_sum[0].item() / chain_sum[1].item()),
                    "max_leapfrogs_of_one_chain": float(chain_max.item()),
-                   "note": "a step cannot end before its longest chain does: a chain is sequential (one warp, ~1.5 us per leapfrog when it "
-                           "runs alone, ~4.5 us while the GPU is full); about one chain in 60 000 adapts to a collapsed step size and runs "
-                           "10-40x the mean (DESIGN.md section 7)"}
+                   "note": "a step cannot end before its longest chain does: a chain is sequential (one warp; measured 1.9 us per leapfrog "
+                           "with the GPU to itself, ~3.4 us averaged over a full batch); about one chain in 60 000 (in the rank-1 shard of the "
+                           "multi-GPU bench: one of 464 068 leapfrogs) adapts to a collapsed step size and runs 10-50x the mean "
+                           "(DESIGN.md section 7, profiles/r01_shard_probe.log)"}
 
     # ---------------- rooflines, CPU baseline (rank 0 only) ----------------
     if rank == 0:
