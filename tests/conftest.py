@@ -95,3 +95,95 @@ def null_posterior_quadrature(k, N, n_grid=500):
     q = 1.0 / (1.0 + np.exp(-U))
     mean_q = (w * q).sum()
     return {"mean_q": mean_q, "var_q": (w * (q - mean_q) ** 2).sum(), "mean_logdelta": mv, "var_logdelta": sv ** 2}
+
+
+_PMD_QUAD_CACHE = {}
+
+
+def pmd_posterior_quadrature(k, N, n_grid=((16, 16, 16, 16, 20), (20, 26, 32))):
+    """Ground truth for the 4-parameter PMD model (fits.py:43-59) by brute-force quadrature, no sampler:
+    q ~ Beta(2,3), A ~ Beta(2,3), c ~ Beta(1,9), delta ~ Exponential(mean 1000), phi = delta + 2,
+    D_z = A (1-q)^(|z|-1) + c, y_z ~ BetaBinomial(D_z phi, (1-D_z) phi, N_z); positions are the first half
+    (forward) then the second half (reverse) of k/N, |z| - 1 = 0..P-1 in each, or one half only.
+    Tensor trapezoid grids in the unconstrained coordinates (logit q, logit A, logit c, log delta) with the
+    Jacobians: axis-aligned passes refined around the mass, then passes along the principal axes; the beta-binomial is scipy.special.betaln, checked
+    against scipy.stats.betabinom on a random subset. Returns posterior means and variances of q, A, c,
+    log delta and D_max = A + c, and the mass on the grid's boundary."""
+    from scipy import special, stats
+    from scipy.special import logsumexp
+
+    k = np.asarray(k, dtype=np.float64)
+    N = np.asarray(N, dtype=np.float64)
+    key = (k.tobytes(), N.tobytes(), repr(n_grid))
+    if key in _PMD_QUAD_CACHE:
+        return _PMD_QUAD_CACHE[key]
+    n_pos = len(k)
+    half = n_pos // 2 if n_pos % 2 == 0 and n_pos > 15 else n_pos
+    x = np.arange(n_pos) % half  # |z| - 1
+    log_c = special.gammaln(N + 1) - special.gammaln(k + 1) - special.gammaln(N - k + 1)
+
+    def log_post(U):  # U: four broadcastable arrays
+        q, A, c = (1.0 / (1.0 + np.exp(-u)) for u in U[:3])
+        d = np.exp(U[3])
+        phi = d + 2.0
+        lp = stats.beta.logpdf(q, 2, 3) + np.log(q) + np.log1p(-q)
+        lp = lp + stats.beta.logpdf(A, 2, 3) + np.log(A) + np.log1p(-A)
+        lp = lp + stats.beta.logpdf(c, 1, 9) + np.log(c) + np.log1p(-c)
+        lp = lp + stats.expon.logpdf(d, scale=1000.0) + U[3]
+        lp = np.broadcast_to(lp, np.broadcast_shapes(*(u.shape for u in U))).copy()
+        bad = np.zeros(lp.shape, bool)
+        for i in range(n_pos):
+            Dz = A * (1.0 - q) ** x[i] + c
+            bad |= np.broadcast_to(Dz >= 1.0, lp.shape)  # clip(Dz, 0, 1) -> beta = 0 -> NaN in the reference: no mass
+            Dz = np.minimum(Dz, 1.0 - 1e-16)
+            a, b = Dz * phi, (1.0 - Dz) * phi
+            lp += special.betaln(k[i] + a, N[i] - k[i] + b) - special.betaln(a, b) + log_c[i]
+        lp[bad] = -np.inf
+        return lp
+
+    # the betaln form IS scipy's beta-binomial pmf
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        i = rng.integers(n_pos)
+        a, b = rng.uniform(0.01, 50), rng.uniform(0.5, 3000)
+        ref = stats.betabinom.logpmf(k[i], N[i], a, b)
+        assert abs(special.betaln(k[i] + a, N[i] - k[i] + b) - special.betaln(a, b) + log_c[i] - ref) < 1e-8 * max(1.0, abs(ref))
+
+    # axis-aligned passes find the mass; the later passes use a grid along the principal axes of the
+    # weighted covariance (q, A and c are strongly correlated at high coverage: an axis-aligned grid
+    # would need its spacing below the CONDITIONAL widths)
+    lo = np.array([-10.0, -12.0, -12.0, -5.0])
+    hi = np.array([8.0, 6.0, 4.0, 13.0])
+    mean, L = None, None
+    for n in n_grid[0]:
+        ax = [np.linspace(lo[j], hi[j], n) for j in range(4)]
+        U = np.meshgrid(*ax, indexing="ij", sparse=True)
+        lp = log_post(U)
+        w = np.exp(lp - logsumexp(lp))
+        mean = np.array([(w * U[j]).sum() for j in range(4)])
+        dev = [U[j] - mean[j] for j in range(4)]
+        cov = np.array([[(w * dev[i] * dev[j]).sum() for j in range(4)] for i in range(4)])
+        space = (hi - lo) / (n - 1)
+        sd = np.maximum(np.sqrt(np.diag(cov)), space)  # a peak between grid points: never shrink below the spacing
+        lo = np.maximum(mean - 7.5 * sd, -30.0)
+        hi = np.minimum(mean + 7.5 * sd, [30.0, 30.0, 30.0, 25.0])
+    L = np.linalg.cholesky(cov + np.diag(space ** 2) * 0.25)
+    for n in n_grid[1]:
+        t = np.linspace(-7.5, 7.5, n)
+        T = np.meshgrid(t, t, t, t, indexing="ij")
+        U = [mean[j] + sum(L[j, i] * T[i] for i in range(j + 1)) for j in range(4)]
+        lp = log_post(U)
+        w = np.exp(lp - logsumexp(lp))
+        mean = np.array([(w * U[j]).sum() for j in range(4)])
+        dev = [U[j] - mean[j] for j in range(4)]
+        cov = np.array([[(w * dev[i] * dev[j]).sum() for j in range(4)] for i in range(4)])
+        L = np.linalg.cholesky(cov)
+    edge = sum(w.take(0, axis=j).sum() + w.take(-1, axis=j).sum() for j in range(4))
+    q, A, c = (1.0 / (1.0 + np.exp(-U[j])) for j in range(3))
+    out = {"edge_mass": float(edge)}
+    for name, v in (("q", q), ("A", A), ("c", c), ("logdelta", U[3]), ("D_max", A + c)):
+        m = float((w * v).sum())
+        out["mean_" + name] = m
+        out["var_" + name] = float((w * (v - m) ** 2).sum())
+    _PMD_QUAD_CACHE[key] = out
+    return out

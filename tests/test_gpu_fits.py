@@ -9,9 +9,9 @@ import os
 import numpy as np
 import pytest
 
-from conftest import mcse_batch_means, null_posterior_quadrature
+from conftest import mcse_batch_means, null_posterior_quadrature, pmd_posterior_quadrature
 from metadamage_b200 import _lib, synthetic as syn
-from test_oracle_nuts import synthetic_taxon
+from test_oracle_nuts import PMD_QUADRATURE_CASES, check_pmd_chain_against_quadrature, synthetic_taxon
 
 pytestmark = pytest.mark.gpu
 
@@ -189,6 +189,23 @@ def test_null_model_chains_match_quadrature(ctx):
             assert abs(ld.mean() - truth["mean_logdelta"]) < 4 * mcse_batch_means(ld) + 1e-12, (i, run, ld.mean(), truth["mean_logdelta"])
             assert abs(q.var() - truth["var_q"]) < 5 * mcse_batch_means((q - q.mean()) ** 2) + 0.02 * truth["var_q"], (i, run, "var q")
             assert abs(ld.var() - truth["var_logdelta"]) < 5 * mcse_batch_means((ld - ld.mean()) ** 2) + 0.02 * truth["var_logdelta"], (i, run)
+
+
+def test_pmd_model_chains_match_quadrature(ctx):
+    """Ground truth without any sampler for the PMD model: its 4-D posterior integrated on tensor grids
+    with scipy's beta-binomial (conftest.pmd_posterior_quadrature). The CUDA chains — all positions
+    (full-warp kernel) and forward-only / reverse-only (the two halves of the half-warp kernel) — must
+    agree within 4 x MCSE in the means and 5 x MCSE + 3 % in the variances of q, A, c, log(delta) and
+    D_max = A + c."""
+    taxa = [synthetic_taxon(seed, **kw) for seed, kw in PMD_QUADRATURE_CASES]
+    tid = np.arange(len(taxa), dtype=np.int64) + 7131
+    k = np.stack([t[0] for t in taxa])
+    N = np.stack([t[1] for t in taxa])
+    got = ctx.fit_batch(tid, k, N, _lib.default_config(num_warmup=500, num_samples=4000, do_map=0), want_samples=True)
+    for i, runs in ((0, ((0, slice(0, 30)), (2, slice(0, 15)))), (1, ((0, slice(0, 30)), (4, slice(15, 30))))):
+        for run, sl in runs:
+            truth = pmd_posterior_quadrature(k[i, sl], N[i, sl])
+            check_pmd_chain_against_quadrature(got["samples"][i, run], truth, (i, run))
 
 
 def test_waic_and_assembly_are_consistent(ctx):

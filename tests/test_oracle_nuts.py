@@ -3,7 +3,7 @@ random-walk Metropolis chain on the same unconstrained log density. Also: determ
 partition-independence property (results depend on (seed, tax_id) only)."""
 import numpy as np
 
-from conftest import mcse_batch_means, null_posterior_quadrature
+from conftest import mcse_batch_means, null_posterior_quadrature, pmd_posterior_quadrature
 
 
 def synthetic_taxon(seed, n_lo=200, n_hi=3000, A=0.25, q=0.35, c=0.02, phi=300.0):
@@ -142,3 +142,30 @@ def test_null_model_nuts_matches_quadrature(oracle):
         assert abs(ld.mean() - truth["mean_logdelta"]) < 4 * mcse_batch_means(ld) + 1e-12, (seed, ld.mean(), truth["mean_logdelta"])
         assert abs(q.var() - truth["var_q"]) < 5 * mcse_batch_means((q - q.mean()) ** 2) + 0.02 * truth["var_q"], (seed, "var q")
         assert abs(ld.var() - truth["var_logdelta"]) < 5 * mcse_batch_means((ld - ld.mean()) ** 2) + 0.02 * truth["var_logdelta"], (seed, "var log delta")
+
+
+PMD_QUADRATURE_CASES = ((31, dict(n_lo=200, n_hi=3000)), (32, dict(n_lo=30, n_hi=300, A=0.15, q=0.5, c=0.03, phi=80.0)))
+
+
+def check_pmd_chain_against_quadrature(samples, truth, tag):
+    """Posterior means within 4 x MCSE and variances within 5 x MCSE + 3 % of the quadrature's, for q, A, c,
+    log(delta) and the headline D_max = A + c (BASELINE tolerance: D-max mean and std within 3 x MCSE of the
+    reference's; here the other side is the exact posterior, and the bound is on one chain's own error)."""
+    assert truth["edge_mass"] < 2e-3, (tag, truth["edge_mass"])
+    cols = {"q": samples[:, 0], "A": samples[:, 1], "c": samples[:, 2], "logdelta": np.log(samples[:, 3] - 2.0),
+            "D_max": samples[:, 1] + samples[:, 2]}
+    for name, v in cols.items():
+        m, var = truth["mean_" + name], truth["var_" + name]
+        assert abs(v.mean() - m) < 4 * mcse_batch_means(v) + 1e-12, (tag, name, v.mean(), m)
+        assert abs(v.var() - var) < 5 * mcse_batch_means((v - v.mean()) ** 2) + 0.03 * var, (tag, name, v.var(), var)
+
+
+def test_pmd_model_nuts_matches_quadrature(oracle):
+    """No sampler on the other side: the PMD model's 4-D posterior (fits.py:43-59) integrated on tensor
+    grids with scipy's beta-binomial (conftest.pmd_posterior_quadrature), at high and at moderate coverage.
+    Pins the restated NUTS, the PMD log density, its bijections and Jacobians to ground truth."""
+    for seed, kw in PMD_QUADRATURE_CASES:
+        k, N = synthetic_taxon(seed, **kw)
+        truth = pmd_posterior_quadrature(k, N)
+        nuts = oracle.nuts_run(k, N, tax_id=7100 + seed, run_kind=0, cfg=oracle.default_config(num_warmup=500, num_samples=4000))
+        check_pmd_chain_against_quadrature(nuts["samples"], truth, seed)
