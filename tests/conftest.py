@@ -94,7 +94,14 @@ def null_posterior_quadrature(k, N, n_grid=500):
         lo_v, hi_v = max(mv - 9 * sv, -30.0), min(mv + 9 * sv, 25.0)
     q = 1.0 / (1.0 + np.exp(-U))
     mean_q = (w * q).sum()
-    return {"mean_q": mean_q, "var_q": (w * (q - mean_q) ** 2).sum(), "mean_logdelta": mv, "var_logdelta": sv ** 2}
+    # exact lppd_i = log E[p(y_i | theta)] and pWAIC_i = Var[log p(y_i | theta)] (fits.py:147-165 in the limit S -> inf)
+    phi = np.exp(V) + 2.0
+    ll = stats.betabinom.logpmf(k[:, None, None], N[:, None, None], (q * phi)[None], ((1 - q) * phi)[None])
+    lppd_i = logsumexp(ll + np.log(np.maximum(w, 1e-300))[None], axis=(1, 2))
+    m1 = (w[None] * ll).sum(axis=(1, 2))
+    pwaic_i = (w[None] * (ll - m1[:, None, None]) ** 2).sum(axis=(1, 2))
+    return {"mean_q": mean_q, "var_q": (w * (q - mean_q) ** 2).sum(), "mean_logdelta": mv, "var_logdelta": sv ** 2,
+            "lppd_i": lppd_i, "pwaic_i": pwaic_i}
 
 
 _PMD_QUAD_CACHE = {}
@@ -121,6 +128,13 @@ def pmd_posterior_quadrature(k, N, n_grid=((16, 16, 16, 16, 20), (20, 26, 32))):
     half = n_pos // 2 if n_pos % 2 == 0 and n_pos > 15 else n_pos
     x = np.arange(n_pos) % half  # |z| - 1
     log_c = special.gammaln(N + 1) - special.gammaln(k + 1) - special.gammaln(N - k + 1)
+
+    def log_lik_i(U, i):
+        q, A, c = (1.0 / (1.0 + np.exp(-u)) for u in U[:3])
+        phi = np.exp(U[3]) + 2.0
+        Dz = np.minimum(A * (1.0 - q) ** x[i] + c, 1.0 - 1e-16)
+        a, b = Dz * phi, (1.0 - Dz) * phi
+        return special.betaln(k[i] + a, N[i] - k[i] + b) - special.betaln(a, b) + log_c[i]
 
     def log_post(U):  # U: four broadcastable arrays
         q, A, c = (1.0 / (1.0 + np.exp(-u)) for u in U[:3])
@@ -185,5 +199,26 @@ def pmd_posterior_quadrature(k, N, n_grid=((16, 16, 16, 16, 20), (20, 26, 32))):
         m = float((w * v).sum())
         out["mean_" + name] = m
         out["var_" + name] = float((w * (v - m) ** 2).sum())
+    # exact lppd_i = log E[p(y_i | theta)] and pWAIC_i = Var[log p(y_i | theta)] (fits.py:147-165 in the limit S -> inf)
+    logw = np.log(np.maximum(w, 1e-300))
+    lppd_i, pwaic_i = np.empty(n_pos), np.empty(n_pos)
+    for i in range(n_pos):
+        ll = log_lik_i(U, i)
+        lppd_i[i] = logsumexp(ll + logw)
+        m1 = (w * ll).sum()
+        pwaic_i[i] = (w * (ll - m1) ** 2).sum()
+    out["lppd_i"], out["pwaic_i"] = lppd_i, pwaic_i
     _PMD_QUAD_CACHE[key] = out
     return out
+
+
+def n_sigma_by_quadrature(k, N):
+    """The reference's D-max significance (fits.py:194-201) from the EXACT per-position WAIC terms of the
+    PMD and the null posterior (quadrature, no sampler)."""
+    pmd, null = pmd_posterior_quadrature(k, N), null_posterior_quadrature(k, N)
+    waic_pmd = -2.0 * (pmd["lppd_i"] - pmd["pwaic_i"])
+    waic_null = -2.0 * (null["lppd_i"] - null["pwaic_i"])
+    n = len(waic_pmd)
+    dse = np.sqrt(n * np.var(waic_pmd - waic_null))
+    return {"n_sigma": (waic_null.sum() - waic_pmd.sum()) / dse, "waic_pmd": waic_pmd.sum(), "waic_null": waic_null.sum(),
+            "D_max_mean": pmd["mean_D_max"], "D_max_std": np.sqrt(pmd["var_D_max"])}

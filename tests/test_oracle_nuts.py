@@ -3,7 +3,7 @@ random-walk Metropolis chain on the same unconstrained log density. Also: determ
 partition-independence property (results depend on (seed, tax_id) only)."""
 import numpy as np
 
-from conftest import mcse_batch_means, null_posterior_quadrature, pmd_posterior_quadrature
+from conftest import mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature
 
 
 def synthetic_taxon(seed, n_lo=200, n_hi=3000, A=0.25, q=0.35, c=0.02, phi=300.0):
@@ -169,3 +169,27 @@ def test_pmd_model_nuts_matches_quadrature(oracle):
         truth = pmd_posterior_quadrature(k, N)
         nuts = oracle.nuts_run(k, N, tax_id=7100 + seed, run_kind=0, cfg=oracle.default_config(num_warmup=500, num_samples=4000))
         check_pmd_chain_against_quadrature(nuts["samples"], truth, seed)
+
+
+N_SIGMA_CASES = PMD_QUADRATURE_CASES + ((33, dict(n_lo=100, n_hi=1000, A=0.02, q=0.5, c=0.02, phi=500.0)),)
+
+
+def check_fit_row_against_exact_posterior(row, truth, tag):
+    """One fitted row (4000 draws) against the exact posterior: the reference's headline outputs n_sigma
+    (fits.py:194-201), the two WAICs (fits.py:147-168) and the marginalised D_max mean / std (fits.py:270)."""
+    assert abs(row["n_sigma"] - truth["n_sigma"]) < 0.05 + 0.03 * abs(truth["n_sigma"]), (tag, row["n_sigma"], truth["n_sigma"])
+    assert abs(row["run"]["waic"][0] - truth["waic_pmd"]) < 1.0, (tag, row["run"]["waic"][0], truth["waic_pmd"])
+    assert abs(row["run"]["waic"][1] - truth["waic_null"]) < 1.0, (tag, row["run"]["waic"][1], truth["waic_null"])
+    assert abs(row["D_max_marginalized_mean"] - truth["D_max_mean"]) < 0.015 * truth["D_max_mean"], (tag, "D_max mean")
+    assert abs(row["D_max_marginalized_std"] - truth["D_max_std"]) < 0.08 * truth["D_max_std"], (tag, "D_max std")
+
+
+def test_n_sigma_and_dmax_match_exact_posterior(oracle):
+    """The path's headline numbers with no sampler on the other side: n_sigma, WAIC and D_max from the exact
+    PMD and null posteriors (quadrature of scipy's beta-binomial) against a full fit of the restated path."""
+    for seed, kw in N_SIGMA_CASES:
+        k, N = synthetic_taxon(seed, **kw)
+        truth = n_sigma_by_quadrature(k, N)
+        cfg = oracle.default_config(num_warmup=500, num_samples=4000, do_fwd_rev=0, do_map=0)
+        row = oracle.fit_batch(np.array([7100 + seed]), k[None], N[None], cfg)["result"][0]
+        check_fit_row_against_exact_posterior(row, truth, seed)
