@@ -107,7 +107,7 @@ def null_posterior_quadrature(k, N, n_grid=500):
 _PMD_QUAD_CACHE = {}
 
 
-def pmd_posterior_quadrature(k, N, n_grid=((16, 16, 16, 16, 20), (20, 26, 32))):
+def pmd_posterior_quadrature(k, N, n_grid=((16, 16, 16, 16, 20), (20, 28))):
     """Ground truth for the 4-parameter PMD model (fits.py:43-59) by brute-force quadrature, no sampler:
     q ~ Beta(2,3), A ~ Beta(2,3), c ~ Beta(1,9), delta ~ Exponential(mean 1000), phi = delta + 2,
     D_z = A (1-q)^(|z|-1) + c, y_z ~ BetaBinomial(D_z phi, (1-D_z) phi, N_z); positions are the first half
@@ -208,6 +208,7 @@ def pmd_posterior_quadrature(k, N, n_grid=((16, 16, 16, 16, 20), (20, 26, 32))):
         m1 = (w * ll).sum()
         pwaic_i[i] = (w * (ll - m1) ** 2).sum()
     out["lppd_i"], out["pwaic_i"] = lppd_i, pwaic_i
+    out["_grid"] = (mean, L, log_post)  # for pmd_predictive_quadrature
     _PMD_QUAD_CACHE[key] = out
     return out
 
@@ -222,3 +223,55 @@ def n_sigma_by_quadrature(k, N):
     dse = np.sqrt(n * np.var(waic_pmd - waic_null))
     return {"n_sigma": (waic_null.sum() - waic_pmd.sum()) / dse, "waic_pmd": waic_pmd.sum(), "waic_null": waic_null.sum(),
             "D_max_mean": pmd["mean_D_max"], "D_max_std": np.sqrt(pmd["var_D_max"])}
+
+
+def pmd_predictive_quadrature(k, N, pos=0, n=20, prob=0.68):
+    """Exact posterior predictive of fits.py:89-120 at one position (default z = 1 forward, the reference's
+    D_max): pmf(y) = E_posterior[BetaBinomial(y; N_pos, D phi, (1 - D) phi)] on a principal-axis grid of the
+    PMD posterior; returns the median and the narrowest interval holding `prob` of the mass (what np.median
+    and numpyro's hpdi converge to as the number of draws grows), as fractions y / N_pos, and the pmf."""
+    from scipy import special
+    from scipy.special import logsumexp
+
+    post = pmd_posterior_quadrature(k, N)
+    mean, L, log_post = post["_grid"]
+    k = np.asarray(k, dtype=np.float64)
+    N = np.asarray(N, dtype=np.float64)
+    n_pos = len(k)
+    half = n_pos // 2 if n_pos % 2 == 0 and n_pos > 15 else n_pos
+    xz = pos % half
+    t = np.linspace(-7.5, 7.5, n)
+    T = np.meshgrid(t, t, t, t, indexing="ij")
+    U = [mean[j] + sum(L[j, i] * T[i] for i in range(j + 1)) for j in range(4)]
+    lp = log_post(U)
+    logw = (lp - logsumexp(lp)).ravel()
+    keep = logw > logw.max() - 40.0
+    logw = logw[keep]
+    q, A, c = (1.0 / (1.0 + np.exp(-U[j].ravel()[keep])) for j in range(3))
+    phi = np.exp(U[3].ravel()[keep]) + 2.0
+    D = np.minimum(A * (1.0 - q) ** xz + c, 1.0 - 1e-16)
+    a, b = D * phi, (1.0 - D) * phi
+    Np = int(N[pos])
+    y = np.arange(Np + 1, dtype=np.float64)
+    log_c = special.gammaln(Np + 1) - special.gammaln(y + 1) - special.gammaln(Np - y + 1)
+    base = logw - special.betaln(a, b)
+    log_pmf = lambda yy: logsumexp(base + special.betaln(yy + a, Np - yy + b)) + log_c[int(yy)]  # noqa: E731
+    # support first (every `step`-th count), then every count inside it
+    step = max(1, Np // 150)
+    coarse = np.array([log_pmf(yy) for yy in y[::step]])
+    live = np.flatnonzero(coarse > coarse.max() - 45.0)
+    y_lo, y_hi = max(0, (live[0] - 1) * step), min(Np, (live[-1] + 1) * step)
+    pmf = np.zeros(Np + 1)
+    pmf[y_lo:y_hi + 1] = np.exp([log_pmf(yy) for yy in y[y_lo:y_hi + 1]])
+    pmf /= pmf.sum()
+    cdf = np.cumsum(pmf)
+    median = int(np.searchsorted(cdf, 0.5))
+    best = (Np + 1, 0, Np)
+    c0 = np.r_[0.0, cdf]
+    for lo in range(Np + 1):
+        hi = int(np.searchsorted(cdf, c0[lo] + prob - 1e-12))
+        if hi <= Np and hi - lo < best[0]:
+            best = (hi - lo, lo, hi)
+    m1 = (pmf * y).sum()
+    return {"median": median / Np, "hpdi_lo": best[1] / Np, "hpdi_hi": best[2] / Np, "pmf": pmf, "N": Np,
+            "sd_counts": float(np.sqrt((pmf * (y - m1) ** 2).sum()))}

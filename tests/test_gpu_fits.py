@@ -9,10 +9,11 @@ import os
 import numpy as np
 import pytest
 
-from conftest import mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature
+from conftest import (mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature,
+                      pmd_predictive_quadrature)
 from metadamage_b200 import _lib, synthetic as syn
 from test_oracle_nuts import (N_SIGMA_CASES, PMD_QUADRATURE_CASES, check_fit_row_against_exact_posterior,
-                              check_pmd_chain_against_quadrature, synthetic_taxon)
+                              check_pmd_chain_against_quadrature, check_predictive_dmax_against_exact, synthetic_taxon)
 
 pytestmark = pytest.mark.gpu
 
@@ -211,7 +212,8 @@ def test_pmd_model_chains_match_quadrature(ctx):
 
 def test_n_sigma_and_dmax_match_exact_posterior(ctx):
     """The path's headline outputs from the CUDA kernels (NUTS + fused WAIC accumulation + assembly) against
-    the exact posterior: n_sigma, the PMD and null WAIC, D_max mean and std by quadrature, no sampler."""
+    the exact posterior: n_sigma, the PMD and null WAIC, D_max mean and std, and the predictive kernel's D_max
+    (median of y_rep / N at z = 1) with its 68 % HPDI against the exact predictive pmf — quadrature, no sampler."""
     taxa = [synthetic_taxon(seed, **kw) for seed, kw in N_SIGMA_CASES]
     tid = np.arange(len(taxa), dtype=np.int64) + 7161
     k = np.stack([t[0] for t in taxa])
@@ -219,6 +221,7 @@ def test_n_sigma_and_dmax_match_exact_posterior(ctx):
     got = ctx.fit_batch(tid, k, N, _lib.default_config(num_warmup=500, num_samples=4000, do_map=0, do_fwd_rev=0))
     for i in range(len(taxa)):
         check_fit_row_against_exact_posterior(got["result"][i], n_sigma_by_quadrature(k[i], N[i]), i)
+        check_predictive_dmax_against_exact(got["result"][i], pmd_predictive_quadrature(k[i], N[i]), 4000, i)
 
 
 def test_waic_and_assembly_are_consistent(ctx):

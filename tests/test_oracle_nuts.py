@@ -3,7 +3,8 @@ random-walk Metropolis chain on the same unconstrained log density. Also: determ
 partition-independence property (results depend on (seed, tax_id) only)."""
 import numpy as np
 
-from conftest import mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature
+from conftest import (mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature,
+                      pmd_predictive_quadrature)
 
 
 def synthetic_taxon(seed, n_lo=200, n_hi=3000, A=0.25, q=0.35, c=0.02, phi=300.0):
@@ -184,12 +185,26 @@ def check_fit_row_against_exact_posterior(row, truth, tag):
     assert abs(row["D_max_marginalized_std"] - truth["D_max_std"]) < 0.08 * truth["D_max_std"], (tag, "D_max std")
 
 
+def check_predictive_dmax_against_exact(row, pred, n_draws, tag):
+    """D_max (median of y_rep / N at z = 1) and its 68 % HPDI (fits.py:112-120, 249-261) against the exact
+    posterior predictive pmf: within the Monte-Carlo error of a median / an interval end of n_draws draws
+    (sd of the pmf over sqrt(n_draws), in counts) plus one resp. two counts of discreteness."""
+    Np, se = pred["N"], pred["sd_counts"] / np.sqrt(n_draws)
+    assert abs(row["D_max"] - pred["median"]) * Np < 1.0 + 5.0 * se, (tag, row["D_max"] * Np, pred["median"] * Np)
+    for got, exact in ((row["D_max_lower_hpdi"], pred["hpdi_lo"]), (row["D_max_upper_hpdi"], pred["hpdi_hi"])):
+        assert abs(got - exact) * Np < 2.0 + 8.0 * se, (tag, got * Np, exact * Np)
+    width, exact_width = (row["D_max_upper_hpdi"] - row["D_max_lower_hpdi"]) * Np, (pred["hpdi_hi"] - pred["hpdi_lo"]) * Np
+    assert abs(width - exact_width) < 2.0 + 8.0 * se, (tag, width, exact_width)
+
+
 def test_n_sigma_and_dmax_match_exact_posterior(oracle):
-    """The path's headline numbers with no sampler on the other side: n_sigma, WAIC and D_max from the exact
-    PMD and null posteriors (quadrature of scipy's beta-binomial) against a full fit of the restated path."""
+    """The path's headline numbers with no sampler on the other side: n_sigma, WAIC, the marginalised D_max and
+    the posterior-predictive D_max with its HPDI from the exact PMD and null posteriors (quadrature of scipy's
+    beta-binomial) against a full fit of the restated path."""
     for seed, kw in N_SIGMA_CASES:
         k, N = synthetic_taxon(seed, **kw)
         truth = n_sigma_by_quadrature(k, N)
         cfg = oracle.default_config(num_warmup=500, num_samples=4000, do_fwd_rev=0, do_map=0)
         row = oracle.fit_batch(np.array([7100 + seed]), k[None], N[None], cfg)["result"][0]
         check_fit_row_against_exact_posterior(row, truth, seed)
+        check_predictive_dmax_against_exact(row, pmd_predictive_quadrature(k, N), 4000, seed)
