@@ -275,3 +275,17 @@ def pmd_predictive_quadrature(k, N, pos=0, n=20, prob=0.68):
     m1 = (pmf * y).sum()
     return {"median": median / Np, "hpdi_lo": best[1] / Np, "hpdi_hi": best[2] / Np, "pmf": pmf, "N": Np,
             "sd_counts": float(np.sqrt((pmf * (y - m1) ** 2).sum()))}
+
+
+def asymmetry_by_quadrature(k, N):
+    """Exact n_sigma_forward, n_sigma_reverse (fits.py:317, 339) and asymmetry (fits.py:204-227, 352): the
+    forward-only and reverse-only refits are the same models on one half of the positions."""
+    k, N = np.asarray(k), np.asarray(N)
+    P = len(k) // 2
+    fwd, rev = n_sigma_by_quadrature(k[:P], N[:P]), n_sigma_by_quadrature(k[P:], N[P:])
+    both = pmd_posterior_quadrature(k, N)
+    pf, pr = pmd_posterior_quadrature(k[:P], N[:P]), pmd_posterior_quadrature(k[P:], N[P:])
+    waic_all = -2.0 * (both["lppd_i"] - both["pwaic_i"])
+    waic_fr = np.r_[-2.0 * (pf["lppd_i"] - pf["pwaic_i"]), -2.0 * (pr["lppd_i"] - pr["pwaic_i"])]
+    dse = np.sqrt(len(waic_all) * np.var(waic_all - waic_fr))
+    return {"n_sigma_forward": fwd["n_sigma"], "n_sigma_reverse": rev["n_sigma"], "asymmetry": (waic_fr.sum() - waic_all.sum()) / dse}

@@ -9,10 +9,10 @@ import os
 import numpy as np
 import pytest
 
-from conftest import (mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature,
+from conftest import (asymmetry_by_quadrature, mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature,
                       pmd_predictive_quadrature)
 from metadamage_b200 import _lib, synthetic as syn
-from test_oracle_nuts import (N_SIGMA_CASES, PMD_QUADRATURE_CASES, check_fit_row_against_exact_posterior,
+from test_oracle_nuts import (N_SIGMA_CASES, PMD_QUADRATURE_CASES, check_asymmetry_against_exact, check_fit_row_against_exact_posterior,
                               check_pmd_chain_against_quadrature, check_predictive_dmax_against_exact, synthetic_taxon)
 
 pytestmark = pytest.mark.gpu
@@ -222,6 +222,15 @@ def test_n_sigma_and_dmax_match_exact_posterior(ctx):
     for i in range(len(taxa)):
         check_fit_row_against_exact_posterior(got["result"][i], n_sigma_by_quadrature(k[i], N[i]), i)
         check_predictive_dmax_against_exact(got["result"][i], pmd_predictive_quadrature(k[i], N[i]), 4000, i)
+
+
+def test_forward_reverse_refits_match_exact_posterior(ctx):
+    """The half-warp kernels' WAIC accumulation and the assembly of n_sigma_forward / n_sigma_reverse /
+    asymmetry (fits.py:298-356) against their exact values by quadrature."""
+    seed, kw = N_SIGMA_CASES[1]
+    k, N = synthetic_taxon(seed, **kw)
+    got = ctx.fit_batch(np.array([7191], np.int64), k[None], N[None], _lib.default_config(num_warmup=500, num_samples=4000, do_map=0))
+    check_asymmetry_against_exact(got["result"][0], asymmetry_by_quadrature(k, N), seed)
 
 
 def test_waic_and_assembly_are_consistent(ctx):

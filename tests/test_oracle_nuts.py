@@ -3,7 +3,7 @@ random-walk Metropolis chain on the same unconstrained log density. Also: determ
 partition-independence property (results depend on (seed, tax_id) only)."""
 import numpy as np
 
-from conftest import (mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature,
+from conftest import (asymmetry_by_quadrature, mcse_batch_means, n_sigma_by_quadrature, null_posterior_quadrature, pmd_posterior_quadrature,
                       pmd_predictive_quadrature)
 
 
@@ -208,3 +208,19 @@ def test_n_sigma_and_dmax_match_exact_posterior(oracle):
         row = oracle.fit_batch(np.array([7100 + seed]), k[None], N[None], cfg)["result"][0]
         check_fit_row_against_exact_posterior(row, truth, seed)
         check_predictive_dmax_against_exact(row, pmd_predictive_quadrature(k, N), 4000, seed)
+
+
+def check_asymmetry_against_exact(row, truth, tag):
+    """n_sigma of the forward-only / reverse-only refits and the asymmetry statistic (fits.py:298-356) against
+    their exact values (a small difference of WAICs: absolute gate 0.2 on the asymmetry)."""
+    for name in ("n_sigma_forward", "n_sigma_reverse"):
+        assert abs(row[name] - truth[name]) < 0.05 + 0.03 * abs(truth[name]), (tag, name, row[name], truth[name])
+    assert abs(row["asymmetry"] - truth["asymmetry"]) < 0.2, (tag, row["asymmetry"], truth["asymmetry"])
+
+
+def test_forward_reverse_refits_match_exact_posterior(oracle):
+    seed, kw = N_SIGMA_CASES[1]
+    k, N = synthetic_taxon(seed, **kw)
+    cfg = oracle.default_config(num_warmup=500, num_samples=4000, do_map=0)
+    row = oracle.fit_batch(np.array([7100 + seed]), k[None], N[None], cfg)["result"][0]
+    check_asymmetry_against_exact(row, asymmetry_by_quadrature(k, N), seed)
