@@ -393,8 +393,8 @@ def main():
     chain_stats = {"mean_leapfrogs_per_chain": float(chain_sum[0].item() / chain_sum[1].item()),
                    "max_leapfrogs_of_one_chain": float(chain_max.item()),
                    "note": "a step cannot end before its longest chain does: a chain is sequential (one warp; measured 1.9 us per leapfrog "
-                           "with the GPU to itself, ~3.4 us averaged over a full batch); about one chain in 60 000 (in the rank-1 shard of the "
-                           "multi-GPU bench: one of 464 068 leapfrogs) adapts to a collapsed step size and runs 10-50x the mean "
+                           "with the GPU to itself, ~3.4 us averaged over a full batch); rarely (one chain in the 480 000 of the eight bench "
+                           "shards: 464 068 leapfrogs, in rank 1's) a chain adapts to a collapsed step size and runs ~50x the mean "
                            "(DESIGN.md section 7, profiles/r01_shard_probe.log)"}
 
     # ---------------- rooflines, CPU baseline (rank 0 only) ----------------
