@@ -224,6 +224,20 @@ def test_n_sigma_and_dmax_match_exact_posterior(ctx):
         check_predictive_dmax_against_exact(got["result"][i], pmd_predictive_quadrature(k[i], N[i]), 4000, i)
 
 
+def test_max_position_25_matches_exact_posterior(ctx):
+    """BASELINE config 4's geometry (--max-position 25: 50 positions, two per lane in the full-warp kernel)
+    against the exact posterior: n_sigma, both WAICs, D_max mean and std by quadrature."""
+    P, A, q, c, phi = 25, 0.2, 0.3, 0.02, 150.0
+    rng = np.random.default_rng(41)
+    N = rng.integers(50, 600, 2 * P).astype(np.uint32)
+    z = np.r_[np.arange(P), np.arange(P)]
+    Dz = A * (1 - q) ** z + c
+    k = rng.binomial(N, rng.beta(Dz * phi, (1 - Dz) * phi)).astype(np.uint32)
+    cfg = _lib.default_config(num_warmup=500, num_samples=4000, do_map=0, do_fwd_rev=0)
+    got = ctx.fit_batch(np.array([7241], np.int64), k[None], N[None], cfg)
+    check_fit_row_against_exact_posterior(got["result"][0], n_sigma_by_quadrature(k, N), "P25")
+
+
 def test_forward_reverse_refits_match_exact_posterior(ctx):
     """The half-warp kernels' WAIC accumulation and the assembly of n_sigma_forward / n_sigma_reverse /
     asymmetry (fits.py:298-356) against their exact values by quadrature."""
