@@ -13,7 +13,8 @@ from conftest import (asymmetry_by_quadrature, mcse_batch_means, n_sigma_by_quad
                       pmd_predictive_quadrature)
 from metadamage_b200 import _lib, synthetic as syn
 from test_oracle_nuts import (N_SIGMA_CASES, PMD_QUADRATURE_CASES, check_asymmetry_against_exact, check_fit_row_against_exact_posterior,
-                              check_pmd_chain_against_quadrature, check_predictive_dmax_against_exact, synthetic_taxon)
+                              check_pmd_chain_against_quadrature, check_predictions_against_exact_pmf,
+                              check_predictive_dmax_against_exact, synthetic_taxon)
 
 pytestmark = pytest.mark.gpu
 
@@ -236,6 +237,16 @@ def test_max_position_25_matches_exact_posterior(ctx):
     cfg = _lib.default_config(num_warmup=500, num_samples=4000, do_map=0, do_fwd_rev=0)
     got = ctx.fit_batch(np.array([7241], np.int64), k[None], N[None], cfg)
     check_fit_row_against_exact_posterior(got["result"][0], n_sigma_by_quadrature(k, N), "P25")
+
+
+def test_fit_predictions_match_exact_predictive(ctx):
+    """The predictive kernel's per-position median and 68 % HPDI (df_fit_predictions, fits.py:632-665) against
+    the exact posterior-predictive pmf at forward and reverse positions near and far from the read end."""
+    seed, kw = N_SIGMA_CASES[1]
+    k, N = synthetic_taxon(seed, **kw)
+    cfg = _lib.default_config(num_warmup=500, num_samples=4000, do_map=0, do_fwd_rev=0)
+    out = ctx.fit_batch(np.array([7192], np.int64), k[None], N[None], cfg)
+    check_predictions_against_exact_pmf(out, k, N, 4000)
 
 
 def test_forward_reverse_refits_match_exact_posterior(ctx):
