@@ -16,15 +16,17 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every buffer is caller-owned; nothing is retained
- *     after a call returns.
+ *     after a call returns (mdg_fit_batch_submit: after the matching mdg_fit_batch_wait returns).
  *   - every function returns MDG_OK (0) or a negative error code; mdg_last_error() gives a
  *     thread-local human-readable message.
  *   - a ctx is bound to one GPU and one CUDA stream and is NOT thread-safe; distinct ctxs
  *     are independent (one host thread or one process per GPU).
  *   - `mem` says where ALL data pointers of that call live: MDG_HOST (pageable or pinned
  *     host memory; the call does H2D, compute, D2H and synchronises) or MDG_DEVICE (device
- *     memory on the ctx's GPU; the call only enqueues work on the ctx stream; scalar
- *     outputs such as out_n_tax are still host pointers and force a stream sync).
+ *     memory on the ctx's GPU). mdg_fit_batch_submit only enqueues work, for either memory
+ *     space (ordered after everything already on the ctx stream); mdg_fit_batch_wait,
+ *     mdg_fit_batch (= submit + wait) and calls with scalar host outputs such as out_n_tax
+ *     synchronise with the host.
  *   - results are a pure function of (tax_id, k, N, cfg): Philox4x32-10 streams are keyed by
  *     (cfg.seed, tax_id) and counted by (run kind, purpose, iteration, draw), so any
  *     partition of a batch over GPUs / calls gives bit-identical per-TaxID results.
@@ -38,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MDG_VERSION 100 /* 0.1.0 */
+#define MDG_VERSION 200 /* 0.2.0 */
 
 enum mdg_status {
     MDG_OK = 0,
@@ -46,7 +48,8 @@ enum mdg_status {
     MDG_ERR_CUDA = -2,             /* CUDA runtime error (message has the detail) */
     MDG_ERR_NOMEM = -3,            /* allocation failed */
     MDG_ERR_SEGMENT_TOO_LONG = -4, /* a TaxID has more rows than MDG_MAX_SEGMENT_ROWS */
-    MDG_ERR_OVERFLOW = -5          /* a reference-base row sum exceeds uint32 (utils.py:338-339) */
+    MDG_ERR_OVERFLOW = -5,         /* a reference-base row sum exceeds uint32 (utils.py:338-339) */
+    MDG_ERR_BUSY = -6              /* mdg_fit_batch_submit: MDG_MAX_INFLIGHT batches are already in flight on this ctx */
 };
 
 enum mdg_memspace { MDG_HOST = 0, MDG_DEVICE = 1 };
@@ -67,7 +70,11 @@ enum mdg_run_kind {
 #define MDG_FIT_FAILED 0x1u        /* no finite initial point found / non-finite summary */
 #define MDG_FIT_MAP_NOT_CONVERGED 0x2u
 #define MDG_FIT_HAS_DIVERGENCES 0x4u /* >=1 divergent transition after warm-up (informational) */
+#define MDG_FIT_BUDGET_EXCEEDED 0x8u /* a run needed more than cfg.max_leapfrogs_per_run gradient evaluations:
+                                      * the bounded-work analogue of the reference's per-fit timeout
+                                      * (fits.py:37-38, 472-474); always set together with MDG_FIT_FAILED */
 
+#define MDG_MAX_INFLIGHT 2         /* batches one ctx keeps in flight between mdg_fit_batch_submit and _wait */
 #define MDG_MAX_POSITION 64        /* max_position supported by the fit kernels */
 #define MDG_MAX_SEGMENT_ROWS 2048  /* rows of one TaxID the counts kernel can hold in one tile */
 
@@ -83,7 +90,9 @@ typedef struct mdg_fit_config {
     int32_t max_tree_depth;
     int32_t do_map;                   /* 1: also run the MAP fit (new deliverable) */
     int32_t do_fwd_rev;               /* 1: the four forward-/reverse-only runs (fits.py:298-356) */
-    int32_t find_heuristic_step_size; /* 1: numpyro 0.4.1 find_reasonable_step_size at init and window ends */
+    int32_t find_heuristic_step_size; /* numpyro's HMC/NUTS(find_heuristic_step_size=...): 1 runs find_reasonable_step_size
+                                       * at initialisation and at every adaptation-window end. Default 0 = numpyro 0.4.1's
+                                       * default (False), which fits.py:382-387 does not override */
     int32_t reference_quirks;         /* 1: D_max_reverse predictive uses the forward N (fits.py:343-348) */
     int32_t pack_half_warps;          /* 1: run fwd+rev chains in the two halves of one warp (P<=16) */
     double target_accept;
@@ -97,6 +106,9 @@ typedef struct mdg_fit_config {
     double c_prior_a, c_prior_b;      /* Beta(1,9)  fits.py:48 */
     double phi_prior_rate;            /* Exponential(rate=1/1000) on delta = phi - phi_min  fits.py:53,65 */
     double phi_min;                   /* 2  fits.py:54,66 */
+    int32_t max_leapfrogs_per_run;    /* 0 = unlimited (default). > 0: a NUTS run that needs more gradient evaluations is
+                                       * abandoned and its TaxID gets MDG_FIT_FAILED | MDG_FIT_BUDGET_EXCEEDED */
+    int32_t reserved0;
 } mdg_fit_config;
 
 /* per-run sampler diagnostics */
@@ -162,6 +174,14 @@ typedef struct mdg_timings {
     uint32_t n_launches;  /* kernels launched by the last call */
     uint32_t reserved;
     uint64_t leapfrogs[MDG_NUM_RUNS]; /* gradient evaluations per run kind, summed over TaxIDs */
+    /* Batches in flight together run their NUTS launches concurrently, so their nuts_ms overlap. nuts_union_ms is
+     * this batch's contribution to the union of all NUTS intervals of the ctx (batches waited for in submission
+     * order): summed over batches it is the time during which at least one NUTS kernel was running.
+     * nuts_begin_ms / nuts_end_ms: first NUTS start / last NUTS end of the batch, in ms since mdg_ctx_create. */
+    float nuts_union_ms;
+    float nuts_begin_ms;
+    float nuts_end_ms;
+    float reserved1;
 } mdg_timings;
 
 int mdg_version(void);
@@ -270,6 +290,28 @@ int mdg_select_top(mdg_ctx* ctx, int mem, int64_t n_rows,
                    const int64_t* tax_id_row, const uint32_t* n_alignments_row, const uint8_t* keep_row,
                    int64_t n_tax, const int64_t* tax_id, const int64_t* first_row, int64_t n_top,
                    uint64_t* out_weight, int64_t* out_index, int64_t* out_n /* host pointer */);
+
+/*
+ * Asynchronous form of mdg_fit_batch: _submit enqueues the whole batch (H2D staging for MDG_HOST, kernels, D2H of
+ * the results) and returns a ticket without waiting for the GPU; _wait blocks until that batch is complete, fills
+ * `out_timings` (optional) and orders later work on the ctx stream after the batch. Up to MDG_MAX_INFLIGHT batches
+ * per ctx may be in flight (MDG_ERR_BUSY otherwise); they run on separate internal streams with separate scratch, so
+ * the next batch starts while the previous one is still finishing its longest chains: a NUTS chain is sequential, and
+ * the tail of a batch is a handful of chains on an otherwise idle GPU. The same overlap is used between the chunks
+ * of one large batch. All buffers (host or device) must stay valid and unmodified until _wait returns; for MDG_HOST
+ * the copies overlap with compute only if the host buffers are pinned. Tickets should be waited for in submission
+ * order. The caller drives one stream of batches per ctx, e.g. the per-file loop of main.py:43-66 or bench steps:
+ *     submit(batch i+1); wait(batch i); consume(batch i); ...
+ */
+int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
+                         const int64_t* tax_id, const uint32_t* k, const uint32_t* N,
+                         const uint32_t* mism12, const double* noise3,
+                         const mdg_fit_config* cfg,
+                         mdg_fit_result* out,
+                         float* out_median, float* out_hpdi_lo, float* out_hpdi_hi,
+                         double* out_samples, double* out_trace, double* out_waic,
+                         int64_t* out_ticket /* host */);
+int mdg_fit_batch_wait(mdg_ctx* ctx, int64_t ticket, mdg_timings* out_timings /* host, optional */);
 
 /* building blocks exported for the parity tests (device evaluation of single functions) */
 

@@ -18,6 +18,7 @@ MDG_DEVICE = 1
 FIT_FAILED = 0x1
 FIT_MAP_NOT_CONVERGED = 0x2
 FIT_HAS_DIVERGENCES = 0x4
+FIT_BUDGET_EXCEEDED = 0x8
 
 
 class FitConfig(C.Structure):
@@ -46,6 +47,8 @@ class FitConfig(C.Structure):
         ("c_prior_b", C.c_double),
         ("phi_prior_rate", C.c_double),
         ("phi_min", C.c_double),
+        ("max_leapfrogs_per_run", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
     def copy(self, **changes):
@@ -70,6 +73,10 @@ class Timings(C.Structure):
         ("n_launches", C.c_uint32),
         ("reserved", C.c_uint32),
         ("leapfrogs", C.c_uint64 * NUM_RUNS),
+        ("nuts_union_ms", C.c_float),
+        ("nuts_begin_ms", C.c_float),
+        ("nuts_end_ms", C.c_float),
+        ("reserved1", C.c_float),
     ]
 
 

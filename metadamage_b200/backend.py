@@ -60,14 +60,19 @@ class Context:
     def synchronize(self):
         _lib.check(self._lib.mdg_ctx_synchronize(self._h))
 
-    def timings(self):
-        t = Timings()
-        _lib.check(self._lib.mdg_ctx_get_timings(self._h, C.byref(t)))
+    @staticmethod
+    def _timings_dict(t):
         return {
             "counts_ms": t.counts_ms, "map_ms": t.map_ms, "nuts_ms": t.nuts_ms, "ppc_ms": t.ppc_ms,
             "assemble_ms": t.assemble_ms, "total_ms": t.total_ms, "n_launches": int(t.n_launches),
-            "leapfrogs": [int(v) for v in t.leapfrogs],
+            "leapfrogs": [int(v) for v in t.leapfrogs], "nuts_union_ms": t.nuts_union_ms,
+            "nuts_begin_ms": t.nuts_begin_ms, "nuts_end_ms": t.nuts_end_ms,
         }
+
+    def timings(self):
+        t = Timings()
+        _lib.check(self._lib.mdg_ctx_get_timings(self._h, C.byref(t)))
+        return self._timings_dict(t)
 
     def fp64_peak_tflops(self):
         out = C.c_double(0)
@@ -235,13 +240,62 @@ class Context:
     def fit_batch_device(self, tax_id, k, N, out, cfg=None, median=None, hpdi_lo=None, hpdi_hi=None,
                          mism12=None, noise3=None):
         """K3-K7 on torch CUDA tensors; `out` is a uint8 CUDA tensor of n_tax*sizeof(mdg_fit_result)."""
+        self.fit_wait(self.fit_submit_device(tax_id, k, N, out, cfg, median, hpdi_lo, hpdi_hi, mism12, noise3))
+
+    # ------------------------------------------------------------------ asynchronous fits (mdg_fit_batch_submit / _wait)
+    def fit_submit_device(self, tax_id, k, N, out, cfg=None, median=None, hpdi_lo=None, hpdi_hi=None,
+                          mism12=None, noise3=None):
+        """Enqueue K3-K7 on torch CUDA tensors and return a ticket; nothing waits for the GPU. The tensors must
+        stay alive and untouched until `fit_wait(ticket)`. At most two batches per Context are in flight."""
         cfg = cfg or _lib.default_config()
         n_tax, R = k.shape
         if out.numel() * out.element_size() < n_tax * FIT_RESULT_DTYPE.itemsize:
             raise ValueError("out buffer too small")
-        _lib.check(self._lib.mdg_fit_batch(
+        ticket = C.c_int64(0)
+        _lib.check(self._lib.mdg_fit_batch_submit(
             self._h, MDG_DEVICE, n_tax, R // 2, _dptr(tax_id), _dptr(k), _dptr(N), _dptr(mism12), _dptr(noise3),
-            C.byref(cfg), _dptr(out), _dptr(median), _dptr(hpdi_lo), _dptr(hpdi_hi), None, None, None))
+            C.byref(cfg), _dptr(out), _dptr(median), _dptr(hpdi_lo), _dptr(hpdi_hi), None, None, None, C.byref(ticket)))
+        keep = (tax_id, k, N, out, median, hpdi_lo, hpdi_hi, mism12, noise3)
+        return {"id": ticket.value, "keep": keep}
+
+    def fit_submit(self, tax_id, k, N, cfg=None, noise3=None, out=None):
+        """Enqueue K3-K7 on host numpy arrays (pinned ones make the copies asynchronous) and return a ticket.
+        `out` (optional): dict with preallocated `result` / `median` / `hpdi_lo` / `hpdi_hi` arrays (e.g. pinned)."""
+        cfg = cfg or _lib.default_config()
+        tax_id = np.ascontiguousarray(tax_id, dtype=np.int64)
+        k = np.ascontiguousarray(k, dtype=np.uint32)
+        N = np.ascontiguousarray(N, dtype=np.uint32)
+        if k.ndim != 2 or k.shape != N.shape or k.shape[0] != len(tax_id) or k.shape[1] % 2:
+            raise ValueError("k and N must be [n_tax][2*max_position]")
+        n_tax, R = k.shape
+        out = out or {}
+
+        def buf(key, shape, dtype):
+            a = out.get(key)
+            if a is not None and a.dtype == dtype and a.flags["C_CONTIGUOUS"] and a.shape[0] >= shape[0] and a.shape[1:] == shape[1:]:
+                return a[: shape[0]]
+            return np.zeros(shape, dtype) if key == "result" else np.empty(shape, dtype)
+
+        res = buf("result", (n_tax,), FIT_RESULT_DTYPE)
+        med, lo, hi = (buf(key, (n_tax, R), np.float32) for key in ("median", "hpdi_lo", "hpdi_hi"))
+        if noise3 is not None:
+            noise3 = np.ascontiguousarray(noise3, dtype=np.float64)
+        ticket = C.c_int64(0)
+        _lib.check(self._lib.mdg_fit_batch_submit(
+            self._h, MDG_HOST, n_tax, R // 2, ptr(tax_id), ptr(k), ptr(N), None, ptr(noise3), C.byref(cfg),
+            ptr(res), ptr(med), ptr(lo), ptr(hi), None, None, None, C.byref(ticket)))
+        return {"id": ticket.value, "keep": (tax_id, k, N, noise3, cfg),
+                "result": dict(result=res, median=med, hpdi_lo=lo, hpdi_hi=hi)}
+
+    def fit_wait(self, ticket):
+        """Block until the batch of `ticket` is complete; returns its result dict (host submits) with the
+        batch's device timings under "timings"."""
+        t = Timings()
+        _lib.check(self._lib.mdg_fit_batch_wait(self._h, C.c_int64(ticket["id"]), C.byref(t)))
+        ticket["keep"] = None
+        res = ticket.get("result") or {}
+        res["timings"] = self._timings_dict(t)
+        return res
 
     # ------------------------------------------------------------------ test hooks
     def lgamma_digamma(self, x):

@@ -54,15 +54,48 @@ constexpr int kNumEvents = 16;
 
 }  // namespace mdg
 
+// One fit lane = the streams, events and scratch of one chunk in flight. Two lanes per ctx: chunk c+1 (of the
+// same batch or of the next submitted batch) starts under the tail of chunk c, which is a handful of long
+// sequential chains on an otherwise idle GPU.
+struct mdg_fit_lane {
+    cudaStream_t main = nullptr, side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {};  // chunk begin, MAP end, NUTS end, predictive end, done (after assembly + D2H)
+    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    mdg::DevBuf rec, map, pred, counters, samples, waic;
+    unsigned long long* h_leap = nullptr;  // pinned [MDG_NUM_RUNS]
+    bool busy = false;
+    int owner = -1;          // ticket slot of the chunk in flight
+    uint32_t launches = 0;
+};
+
+// One submitted batch (mdg_fit_batch_submit): staging buffers for MDG_HOST and the accumulated timings.
+struct mdg_fit_ticket_slot {
+    bool active = false;
+    int64_t id = 0;
+    cudaEvent_t ev_begin = nullptr;
+    mdg::DevBuf in_tax, in_k, in_N, in_m12, in_noise, out_res, out_med, smp, trace, waic;
+    mdg_timings t = {};
+    double nuts_begin_ms = 0, nuts_end_ms = 0;
+    bool have_nuts = false;
+};
+
+constexpr int kFitLanes = 2;
+constexpr int kFitTickets = 2;
+
 struct mdg_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[mdg::kNumEvents] = {};
-    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t epoch = nullptr;       // time zero of mdg_timings.nuts_begin_ms / nuts_end_ms
+    cudaEvent_t inputs_ready = nullptr;
     mdg::DevBuf buf[mdg::kNumBufs];
+    mdg_fit_lane lane[kFitLanes];
+    mdg_fit_ticket_slot ticket[kFitTickets];
+    int next_lane = 0;
+    int64_t next_ticket_id = 1;
+    double nuts_covered_until_ms = 0;  // union of NUTS intervals harvested so far ends here
     mdg_timings timings = {};
 };
 
@@ -195,6 +228,8 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
 
 extern "C" {
 
+void mdg_ctx_destroy(mdg_ctx* ctx);
+
 int mdg_version(void) { return MDG_VERSION; }
 
 const char* mdg_last_error(void) { return g_error; }
@@ -215,7 +250,7 @@ void mdg_fit_config_default(mdg_fit_config* c) {
     c->max_tree_depth = 10;
     c->do_map = 1;
     c->do_fwd_rev = 1;
-    c->find_heuristic_step_size = 1;
+    c->find_heuristic_step_size = 0;  // numpyro 0.4.1 default (HMC/NUTS(find_heuristic_step_size=False)); fits.py:382-387 passes no override
     c->reference_quirks = 1;
     c->pack_half_warps = 1;
     c->target_accept = 0.8;
@@ -246,15 +281,39 @@ int mdg_ctx_create(int device, mdg_ctx** out) {
                   prop.major, prop.minor);
         return MDG_ERR_CUDA;
     }
+    *out = nullptr;
     mdg_ctx* ctx = new mdg_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    MDG_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    // any failure below releases what was created so far (mdg_ctx_destroy tolerates null members)
+    auto fail = [&](cudaError_t e, const char* what) {
+        set_error("mdg_ctx_create: %s failed: %s", what, cudaGetErrorString(e));
+        mdg_ctx_destroy(ctx);
+        return MDG_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
     ctx->stream = ctx->own_stream;
-    for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
-    for (int i = 0; i < kNumEvents; ++i) MDG_CUDA_TRY(cudaEventCreate(&ctx->ev[i]));
-    MDG_CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-    for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < kNumEvents; ++i)
+        if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->epoch)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->inputs_ready, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    for (auto& ln : ctx->lane) {
+        if ((e = cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+        for (int i = 0; i < 3; ++i)
+            if ((e = cudaStreamCreateWithFlags(&ln.side[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+        for (int i = 0; i < 5; ++i)
+            if ((e = cudaEventCreate(&ln.ev[i])) != cudaSuccess) return fail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&ln.fork_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+        for (int i = 0; i < 3; ++i)
+            if ((e = cudaEventCreateWithFlags(&ln.join_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+        if ((e = cudaHostAlloc((void**)&ln.h_leap, MDG_NUM_RUNS * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess)
+            return fail(e, "cudaHostAlloc");
+    }
+    for (auto& tk : ctx->ticket)
+        if ((e = cudaEventCreate(&tk.ev_begin)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventRecord(ctx->epoch, ctx->own_stream)) != cudaSuccess) return fail(e, "cudaEventRecord");
+    if ((e = cudaEventSynchronize(ctx->epoch)) != cudaSuccess) return fail(e, "cudaEventSynchronize");
     *out = ctx;
     return MDG_OK;
 }
@@ -262,13 +321,30 @@ int mdg_ctx_create(int device, mdg_ctx** out) {
 void mdg_ctx_destroy(mdg_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    for (auto& ln : ctx->lane) {
+        if (ln.main) cudaStreamSynchronize(ln.main);
+        for (int i = 0; i < 3; ++i) if (ln.side[i]) cudaStreamSynchronize(ln.side[i]);
+    }
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->buf) b.release();
     for (int i = 0; i < kNumEvents; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
-    for (int i = 0; i < 3; ++i) {
-        if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
-        if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->epoch) cudaEventDestroy(ctx->epoch);
+    if (ctx->inputs_ready) cudaEventDestroy(ctx->inputs_ready);
+    for (auto& ln : ctx->lane) {
+        for (mdg::DevBuf* b : {&ln.rec, &ln.map, &ln.pred, &ln.counters, &ln.samples, &ln.waic}) b->release();
+        for (int i = 0; i < 5; ++i) if (ln.ev[i]) cudaEventDestroy(ln.ev[i]);
+        if (ln.fork_ev) cudaEventDestroy(ln.fork_ev);
+        for (int i = 0; i < 3; ++i) {
+            if (ln.join_ev[i]) cudaEventDestroy(ln.join_ev[i]);
+            if (ln.side[i]) cudaStreamDestroy(ln.side[i]);
+        }
+        if (ln.main) cudaStreamDestroy(ln.main);
+        if (ln.h_leap) cudaFreeHost(ln.h_leap);
+    }
+    for (auto& tk : ctx->ticket) {
+        for (mdg::DevBuf* b : {&tk.in_tax, &tk.in_k, &tk.in_N, &tk.in_m12, &tk.in_noise, &tk.out_res, &tk.out_med, &tk.smp, &tk.trace, &tk.waic})
+            b->release();
+        if (tk.ev_begin) cudaEventDestroy(tk.ev_begin);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -283,6 +359,7 @@ int mdg_ctx_set_stream(mdg_ctx* ctx, void* cuda_stream) {
 int mdg_ctx_synchronize(mdg_ctx* ctx) {
     if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
     DeviceGuard guard(ctx->device);
+    for (auto& ln : ctx->lane) MDG_CUDA_TRY(cudaStreamSynchronize(ln.main));
     MDG_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return MDG_OK;
 }
@@ -736,36 +813,85 @@ int mdg_select_top(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_id_
 // ---------------------------------------------------------------------------------------------
 // K3-K7
 // ---------------------------------------------------------------------------------------------
-int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const int64_t* tax_id, const uint32_t* k,
-                  const uint32_t* N, const uint32_t* mism12, const double* noise3, const mdg_fit_config* cfg,
-                  mdg_fit_result* out, float* out_median, float* out_hpdi_lo, float* out_hpdi_hi,
-                  double* out_samples, double* out_trace, double* out_waic) {
+}  // extern "C"
+
+namespace {
+
+double ms_since_epoch(mdg_ctx* ctx, cudaEvent_t ev) { return (double)elapsed(ctx->epoch, ev); }
+
+// Wait (on the host) for the chunk in flight on a lane and book its CUDA-event times on its ticket.
+int harvest_lane(mdg_ctx* ctx, mdg_fit_lane& ln) {
+    if (!ln.busy) return MDG_OK;
+    MDG_CUDA_TRY(cudaEventSynchronize(ln.ev[4]));
+    mdg_fit_ticket_slot& tk = ctx->ticket[ln.owner];
+    tk.t.map_ms += elapsed(ln.ev[0], ln.ev[1]);
+    tk.t.nuts_ms += elapsed(ln.ev[1], ln.ev[2]);
+    tk.t.ppc_ms += elapsed(ln.ev[2], ln.ev[3]);
+    tk.t.assemble_ms += elapsed(ln.ev[3], ln.ev[4]);
+    tk.t.total_ms = std::max(tk.t.total_ms, elapsed(tk.ev_begin, ln.ev[4]));
+    tk.t.n_launches += ln.launches;
+    for (int r = 0; r < MDG_NUM_RUNS; ++r) tk.t.leapfrogs[r] += ln.h_leap[r];
+    // NUTS-active time as a union of intervals over everything harvested on this ctx (chunks of overlapping
+    // batches run their NUTS launches concurrently; chunks are harvested in submission order)
+    const double a = ms_since_epoch(ctx, ln.ev[1]), b = ms_since_epoch(ctx, ln.ev[2]);
+    tk.t.nuts_union_ms += (float)std::max(0.0, b - std::max(a, ctx->nuts_covered_until_ms));
+    ctx->nuts_covered_until_ms = std::max(ctx->nuts_covered_until_ms, b);
+    if (!tk.have_nuts) { tk.nuts_begin_ms = a; tk.nuts_end_ms = b; tk.have_nuts = true; }
+    tk.nuts_begin_ms = std::min(tk.nuts_begin_ms, a);
+    tk.nuts_end_ms = std::max(tk.nuts_end_ms, b);
+    ln.busy = false;
+    ln.owner = -1;
+    return MDG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const int64_t* tax_id, const uint32_t* k,
+                         const uint32_t* N, const uint32_t* mism12, const double* noise3, const mdg_fit_config* cfg,
+                         mdg_fit_result* out, float* out_median, float* out_hpdi_lo, float* out_hpdi_hi,
+                         double* out_samples, double* out_trace, double* out_waic, int64_t* out_ticket) {
     if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
-    if (!cfg || n_tax < 0 || max_position < 1 || max_position > MDG_MAX_POSITION || (mem != MDG_HOST && mem != MDG_DEVICE)) {
+    if (!cfg || !out_ticket || n_tax < 0 || max_position < 1 || max_position > MDG_MAX_POSITION || (mem != MDG_HOST && mem != MDG_DEVICE)) {
         set_error("mdg_fit_batch: invalid argument");
         return MDG_ERR_INVALID;
     }
     if (cfg->num_samples < 1 || cfg->num_samples > 4096 || cfg->num_warmup < 0 || cfg->max_tree_depth < 1 ||
-        cfg->max_tree_depth > kMaxTreeDepth) {
-        set_error("mdg_fit_batch: need 1 <= num_samples <= 4096, num_warmup >= 0, 1 <= max_tree_depth <= %d", kMaxTreeDepth);
+        cfg->max_tree_depth > kMaxTreeDepth || cfg->max_leapfrogs_per_run < 0) {
+        set_error("mdg_fit_batch: need 1 <= num_samples <= 4096, num_warmup >= 0, 1 <= max_tree_depth <= %d, max_leapfrogs_per_run >= 0",
+                  kMaxTreeDepth);
         return MDG_ERR_INVALID;
     }
     if (n_tax > 0 && (!tax_id || !k || !N || !out)) { set_error("mdg_fit_batch: NULL tax_id/k/N/out"); return MDG_ERR_INVALID; }
+    int slot = -1;
+    for (int i = 0; i < kFitTickets; ++i) if (!ctx->ticket[i].active) { slot = i; break; }
+    if (slot < 0) {
+        set_error("mdg_fit_batch_submit: %d batches are already in flight on this ctx; call mdg_fit_batch_wait first", kFitTickets);
+        return MDG_ERR_BUSY;
+    }
     DeviceGuard guard(ctx->device);
     cudaStream_t st = ctx->stream;
-    ctx->timings = mdg_timings{};
+    mdg_fit_ticket_slot& tk = ctx->ticket[slot];
+    tk.t = mdg_timings{};
+    tk.have_nuts = false;
+    tk.nuts_begin_ms = tk.nuts_end_ms = 0;
+    tk.id = ctx->next_ticket_id++;
+    tk.active = true;
+    *out_ticket = tk.id;
+    MDG_CUDA_TRY(cudaEventRecord(tk.ev_begin, st));
     if (n_tax == 0) return MDG_OK;
     const int P = max_position, R = 2 * P, S = cfg->num_samples, W = cfg->num_warmup;
     const bool host = (mem == MDG_HOST);
     const bool fwd_rev = cfg->do_fwd_rev != 0;
     const bool pack = fwd_rev && cfg->pack_half_warps && P <= 16;
     const Priors pr = make_priors(*cfg);
-    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
     const int sample_runs = out_samples ? MDG_NUM_RUNS : (fwd_rev ? 3 : 1);
     const int items_per_tax = R + (fwd_rev ? 2 : 0);
-    // TaxIDs per chunk: every chunk ends with the tail of its four NUTS launches, so chunks are as
-    // large as ~8 GB of scratch allows (posterior draws dominate: 96 KB per TaxID at S = 1000)
+    // TaxIDs per chunk: every chunk ends with the tail of its four NUTS launches (the next chunk starts under
+    // it on the other lane), so chunks are as large as ~8 GB of scratch per lane allows (posterior draws
+    // dominate: 96 KB per TaxID at S = 1000)
     long long chunk_cap = 65536;
     {
         const size_t per_tax = (size_t)sample_runs * S * 4 * 8 + (size_t)MDG_NUM_RUNS * (sizeof(RunRecord) + 2 * R * 8) +
@@ -775,59 +901,52 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const 
     }
     const long long chunk_max = std::min<long long>(n_tax, chunk_cap);
 
-    // ---- device buffers ----
-    // persistent scratch (per chunk)
+    // ---- staged inputs / outputs for MDG_HOST (whole batch, owned by the ticket) ----
     int rc;
-    if ((rc = ctx->buf[4].ensure((size_t)chunk_max * MDG_NUM_RUNS * sizeof(RunRecord)))) return rc;
-    if ((rc = ctx->buf[5].ensure((size_t)chunk_max * 2 * sizeof(MapRecord)))) return rc;
-    if ((rc = ctx->buf[6].ensure((size_t)chunk_max * items_per_tax * 3 * sizeof(double)))) return rc;
-    if ((rc = ctx->buf[7].ensure(256))) return rc;  // work counters + leapfrog totals
-    if (!out_samples && (rc = ctx->buf[8].ensure((size_t)chunk_max * sample_runs * S * 4 * sizeof(double)))) return rc;
-    if (!out_waic && (rc = ctx->buf[9].ensure((size_t)chunk_max * MDG_NUM_RUNS * 2 * R * sizeof(double)))) return rc;
-    // staged inputs / outputs for MDG_HOST (whole batch)
     const int64_t* d_tax = tax_id; const uint32_t* d_k = k; const uint32_t* d_N = N; const uint32_t* d_m12 = mism12;
     const double* d_noise = noise3;
     mdg_fit_result* d_out = out; float* d_med = out_median; float* d_lo = out_hpdi_lo; float* d_hi = out_hpdi_hi;
     double* d_samples = out_samples; double* d_trace = out_trace; double* d_waic_user = out_waic;
     const size_t nt = (size_t)n_tax;
+    auto bail = [&](int code) { tk.active = false; return code; };
     if (host) {
-        if ((rc = ctx->buf[10].ensure(nt * 8))) return rc;
-        if ((rc = ctx->buf[11].ensure(nt * R * 4))) return rc;
-        if ((rc = ctx->buf[12].ensure(nt * R * 4))) return rc;
-        MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[10].ptr, tax_id, nt * 8, cudaMemcpyHostToDevice, st));
-        MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[11].ptr, k, nt * R * 4, cudaMemcpyHostToDevice, st));
-        MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[12].ptr, N, nt * R * 4, cudaMemcpyHostToDevice, st));
-        d_tax = ctx->buf[10].as<int64_t>(); d_k = ctx->buf[11].as<uint32_t>(); d_N = ctx->buf[12].as<uint32_t>();
+        if ((rc = tk.in_tax.ensure(nt * 8))) return bail(rc);
+        if ((rc = tk.in_k.ensure(nt * R * 4))) return bail(rc);
+        if ((rc = tk.in_N.ensure(nt * R * 4))) return bail(rc);
+        MDG_CUDA_TRY(cudaMemcpyAsync(tk.in_tax.ptr, tax_id, nt * 8, cudaMemcpyHostToDevice, st));
+        MDG_CUDA_TRY(cudaMemcpyAsync(tk.in_k.ptr, k, nt * R * 4, cudaMemcpyHostToDevice, st));
+        MDG_CUDA_TRY(cudaMemcpyAsync(tk.in_N.ptr, N, nt * R * 4, cudaMemcpyHostToDevice, st));
+        d_tax = tk.in_tax.as<int64_t>(); d_k = tk.in_k.as<uint32_t>(); d_N = tk.in_N.as<uint32_t>();
         if (mism12) {
-            if ((rc = ctx->buf[13].ensure(nt * R * 12 * 4))) return rc;
-            MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[13].ptr, mism12, nt * R * 12 * 4, cudaMemcpyHostToDevice, st));
-            d_m12 = ctx->buf[13].as<uint32_t>();
+            if ((rc = tk.in_m12.ensure(nt * R * 12 * 4))) return bail(rc);
+            MDG_CUDA_TRY(cudaMemcpyAsync(tk.in_m12.ptr, mism12, nt * R * 12 * 4, cudaMemcpyHostToDevice, st));
+            d_m12 = tk.in_m12.as<uint32_t>();
         }
         if (noise3) {
-            if ((rc = ctx->buf[14].ensure(nt * 24))) return rc;
-            MDG_CUDA_TRY(cudaMemcpyAsync(ctx->buf[14].ptr, noise3, nt * 24, cudaMemcpyHostToDevice, st));
-            d_noise = ctx->buf[14].as<double>();
+            if ((rc = tk.in_noise.ensure(nt * 24))) return bail(rc);
+            MDG_CUDA_TRY(cudaMemcpyAsync(tk.in_noise.ptr, noise3, nt * 24, cudaMemcpyHostToDevice, st));
+            d_noise = tk.in_noise.as<double>();
         }
-        if ((rc = ctx->buf[15].ensure(nt * sizeof(mdg_fit_result)))) return rc;
-        d_out = ctx->buf[15].as<mdg_fit_result>();
-        if ((rc = ctx->buf[16].ensure(nt * R * 4 * 3))) return rc;
-        d_med = ctx->buf[16].as<float>(); d_lo = d_med + nt * R; d_hi = d_lo + nt * R;
+        if ((rc = tk.out_res.ensure(nt * sizeof(mdg_fit_result)))) return bail(rc);
+        d_out = tk.out_res.as<mdg_fit_result>();
+        if ((rc = tk.out_med.ensure(nt * R * 4 * 3))) return bail(rc);
+        d_med = tk.out_med.as<float>(); d_lo = d_med + nt * R; d_hi = d_lo + nt * R;
         if (out_samples) {
-            if ((rc = ctx->buf[17].ensure(nt * MDG_NUM_RUNS * S * 4 * 8))) return rc;
-            d_samples = ctx->buf[17].as<double>();
+            if ((rc = tk.smp.ensure(nt * MDG_NUM_RUNS * S * 4 * 8))) return bail(rc);
+            d_samples = tk.smp.as<double>();
         }
         if (out_trace) {
-            if ((rc = ctx->buf[18].ensure(nt * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8))) return rc;
-            d_trace = ctx->buf[18].as<double>();
+            if ((rc = tk.trace.ensure(nt * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8))) return bail(rc);
+            d_trace = tk.trace.as<double>();
         }
         if (out_waic) {
-            if ((rc = ctx->buf[19].ensure(nt * MDG_NUM_RUNS * 2 * R * 8))) return rc;
-            d_waic_user = ctx->buf[19].as<double>();
+            if ((rc = tk.waic.ensure(nt * MDG_NUM_RUNS * 2 * R * 8))) return bail(rc);
+            d_waic_user = tk.waic.as<double>();
         }
     } else {
         if (!d_med || !d_lo || !d_hi) {
-            if ((rc = ctx->buf[16].ensure(nt * R * 4 * 3))) return rc;
-            float* base = ctx->buf[16].as<float>();
+            if ((rc = tk.out_med.ensure(nt * R * 4 * 3))) return bail(rc);
+            float* base = tk.out_med.as<float>();
             if (!d_med) d_med = base;
             if (!d_lo) d_lo = base + nt * R;
             if (!d_hi) d_hi = base + 2 * nt * R;
@@ -835,32 +954,45 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const 
     }
     if (d_trace) MDG_CUDA_TRY(cudaMemsetAsync(d_trace, 0xFF, nt * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8, st));
     if (out_samples) MDG_CUDA_TRY(cudaMemsetAsync(d_samples, 0xFF, nt * MDG_NUM_RUNS * (size_t)S * 4 * 8, st));
+    // everything enqueued so far on the ctx stream (the caller's producers of the inputs, the copies above)
+    // precedes the chunks, which run on the lanes' own streams
+    MDG_CUDA_TRY(cudaEventRecord(ctx->inputs_ready, st));
 
-    unsigned int* d_counters = ctx->buf[7].as<unsigned int>();                       // [8]
-    unsigned long long* d_leap = reinterpret_cast<unsigned long long*>(d_counters + 16);  // [6]
-    MDG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 256, st));
-
-    float map_ms = 0, nuts_ms = 0, ppc_ms = 0, asm_ms = 0;
     for (long long c0 = 0; c0 < n_tax; c0 += chunk_cap) {
         const int nc = (int)std::min<long long>(chunk_cap, n_tax - c0);
-        RunRecord* d_rec = ctx->buf[4].as<RunRecord>();
-        MapRecord* d_map = ctx->buf[5].as<MapRecord>();
-        double* d_pred = ctx->buf[6].as<double>();
-        double* d_waic = d_waic_user ? d_waic_user + (size_t)c0 * MDG_NUM_RUNS * 2 * R : ctx->buf[9].as<double>();
-        double* d_smp = out_samples ? d_samples + (size_t)c0 * MDG_NUM_RUNS * S * 4 : ctx->buf[8].as<double>();
-        MDG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 64, st));
-        MDG_CUDA_TRY(cudaMemsetAsync(d_waic, 0, (size_t)nc * MDG_NUM_RUNS * 2 * R * 8, st));
-        MDG_CUDA_TRY(cudaMemsetAsync(d_rec, 0, (size_t)nc * MDG_NUM_RUNS * sizeof(RunRecord), st));
+        mdg_fit_lane& ln = ctx->lane[ctx->next_lane];
+        ctx->next_lane = (ctx->next_lane + 1) % kFitLanes;
+        if ((rc = harvest_lane(ctx, ln))) return bail(rc);  // the lane's previous chunk (host wait only if it is still running)
+        // ---- per-lane scratch ----
+        if ((rc = ln.rec.ensure((size_t)chunk_max * MDG_NUM_RUNS * sizeof(RunRecord)))) return bail(rc);
+        if ((rc = ln.map.ensure((size_t)chunk_max * 2 * sizeof(MapRecord)))) return bail(rc);
+        if ((rc = ln.pred.ensure((size_t)chunk_max * items_per_tax * 3 * sizeof(double)))) return bail(rc);
+        if ((rc = ln.counters.ensure(256))) return bail(rc);  // work counters + leapfrog totals
+        if (!out_samples && (rc = ln.samples.ensure((size_t)chunk_max * sample_runs * S * 4 * sizeof(double)))) return bail(rc);
+        if (!out_waic && (rc = ln.waic.ensure((size_t)chunk_max * MDG_NUM_RUNS * 2 * R * sizeof(double)))) return bail(rc);
+        cudaStream_t ls = ln.main;
+        const uint32_t launches_before = ctx->timings.n_launches;
+        MDG_CUDA_TRY(cudaStreamWaitEvent(ls, ctx->inputs_ready, 0));
+        unsigned int* d_counters = ln.counters.as<unsigned int>();                            // [8]
+        unsigned long long* d_leap = reinterpret_cast<unsigned long long*>(d_counters + 16);  // [6]
+        RunRecord* d_rec = ln.rec.as<RunRecord>();
+        MapRecord* d_map = ln.map.as<MapRecord>();
+        double* d_pred = ln.pred.as<double>();
+        double* d_waic = d_waic_user ? d_waic_user + (size_t)c0 * MDG_NUM_RUNS * 2 * R : ln.waic.as<double>();
+        double* d_smp = out_samples ? d_samples + (size_t)c0 * MDG_NUM_RUNS * S * 4 : ln.samples.as<double>();
+        MDG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 256, ls));
+        MDG_CUDA_TRY(cudaMemsetAsync(d_waic, 0, (size_t)nc * MDG_NUM_RUNS * 2 * R * 8, ls));
+        MDG_CUDA_TRY(cudaMemsetAsync(d_rec, 0, (size_t)nc * MDG_NUM_RUNS * sizeof(RunRecord), ls));
 
         // ---- K3 MAP ----
-        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+        MDG_CUDA_TRY(cudaEventRecord(ln.ev[0], ls));
         if (cfg->do_map) {
             MapLaunch ml = {};
             ml.tax_id = d_tax + c0; ml.k = d_k + (size_t)c0 * R; ml.N = d_N + (size_t)c0 * R;
             ml.n_tax = nc; ml.P = P; ml.pr = pr; ml.work_counter = d_counters + 0; ml.rec = d_map;
-            if ((rc = launch_map(ctx, st, ml, npl_for(R, 32)))) return rc;
+            if ((rc = launch_map(ctx, ls, ml, npl_for(R, 32)))) return bail(rc);
         }
-        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
+        MDG_CUDA_TRY(cudaEventRecord(ln.ev[1], ls));
 
         // ---- K4 NUTS: four launches on four streams (they share the SMs as CTAs retire) ----
         FitLaunch fl = {};
@@ -870,14 +1002,13 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const 
         fl.rec = d_rec; fl.waic = d_waic; fl.samples = d_smp; fl.sample_runs = sample_runs;
         fl.trace = d_trace ? d_trace + (size_t)c0 * MDG_NUM_RUNS * (W + S) * 4 : nullptr;
         for (int r = 0; r < MDG_NUM_RUNS; ++r) fl.sample_slot[r] = out_samples ? r : ((r & 1) ? -1 : r / 2);
-        MDG_CUDA_TRY(cudaEventRecord(ctx->fork_ev, st));
-        for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0));
+        MDG_CUDA_TRY(cudaEventRecord(ln.fork_ev, ls));
+        for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaStreamWaitEvent(ln.side[i], ln.fork_ev, 0));
         {
             // Launch order = dispatch order of the persistent CTAs: the kernels share the SMs as CTAs
             // retire, so the whole step behaves like one list schedule over all (TaxID, run) items.
             // PMD chains are long and heavy-tailed (adapted step size; max ~8x the mean), null chains
-            // short and uniform: PMD first, null last fills the tail (measured chain lengths + list-
-            // schedule simulation: 21.6 % -> 2.6 % idle; profiles/r01_nuts_tuning.md).
+            // short and uniform: PMD first, null last fills the tail (profiles/r01_nuts_tuning.md).
             FitLaunch a = fl;  // PMD, all positions
             a.n_masks = 1; a.mask0 = 0; a.n_items = nc; a.work_counter = d_counters + 1;
             FitLaunch b = fl;  // null, all positions
@@ -890,16 +1021,16 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const 
                 c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_masks = 2; d.n_masks = 2; c.mask0 = 1; d.mask0 = 1;
             }
             const int npl_half = pack ? 1 : npl_for(P, 32), gw_half = pack ? 16 : 32;
-            if (fwd_rev && (rc = launch_nuts_dispatch<0>(ctx, ctx->side[1], c, npl_half, gw_half))) return rc;
-            if ((rc = launch_nuts_dispatch<0>(ctx, st, a, npl_for(R, 32), 32))) return rc;
-            if (fwd_rev && (rc = launch_nuts_dispatch<1>(ctx, ctx->side[2], d, npl_half, gw_half))) return rc;
-            if ((rc = launch_nuts_dispatch<1>(ctx, ctx->side[0], b, npl_for(R, 32), 32))) return rc;
+            if (fwd_rev && (rc = launch_nuts_dispatch<0>(ctx, ln.side[1], c, npl_half, gw_half))) return bail(rc);
+            if ((rc = launch_nuts_dispatch<0>(ctx, ls, a, npl_for(R, 32), 32))) return bail(rc);
+            if (fwd_rev && (rc = launch_nuts_dispatch<1>(ctx, ln.side[2], d, npl_half, gw_half))) return bail(rc);
+            if ((rc = launch_nuts_dispatch<1>(ctx, ln.side[0], b, npl_for(R, 32), 32))) return bail(rc);
         }
         for (int i = 0; i < 3; ++i) {
-            MDG_CUDA_TRY(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
-            MDG_CUDA_TRY(cudaStreamWaitEvent(st, ctx->join_ev[i], 0));
+            MDG_CUDA_TRY(cudaEventRecord(ln.join_ev[i], ln.side[i]));
+            MDG_CUDA_TRY(cudaStreamWaitEvent(ls, ln.join_ev[i], 0));
         }
-        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[6], st));
+        MDG_CUDA_TRY(cudaEventRecord(ln.ev[2], ls));
 
         // ---- K6 posterior predictive ----
         {
@@ -915,11 +1046,11 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const 
             const size_t smem = (size_t)kPpcWarps * sp * 4;
             MDG_CUDA_TRY(cudaFuncSetAttribute(ppc_kernel<kPpcWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int grid = persistent_grid(ppc_kernel<kPpcWarps>, kPpcWarps * 32, smem, ctx->num_sms, (long long)nc * items_per_tax, kPpcWarps);
-            ppc_kernel<kPpcWarps><<<grid, kPpcWarps * 32, smem, st>>>(pl);
+            ppc_kernel<kPpcWarps><<<grid, kPpcWarps * 32, smem, ls>>>(pl);
             MDG_CUDA_TRY(cudaGetLastError());
             ctx->timings.n_launches++;
         }
-        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[7], st));
+        MDG_CUDA_TRY(cudaEventRecord(ln.ev[3], ls));
 
         // ---- K5/K7 assembly ----
         {
@@ -931,40 +1062,65 @@ int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const 
             al.waic = d_waic; al.pred = d_pred; al.items_per_tax = items_per_tax;
             al.out = d_out + c0; al.out_median = d_med + (size_t)c0 * R; al.out_lo = d_lo + (size_t)c0 * R;
             al.out_hi = d_hi + (size_t)c0 * R; al.leapfrog_totals = d_leap;
-            assemble_kernel<<<(nc + 127) / 128, 128, 0, st>>>(al);
+            assemble_kernel<<<(nc + 127) / 128, 128, 0, ls>>>(al);
             MDG_CUDA_TRY(cudaGetLastError());
             ctx->timings.n_launches++;
         }
-        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[8], st));
-        // per-chunk timing needs the events to have completed; chunks are seconds long, so the
-        // sync costs nothing measurable
-        MDG_CUDA_TRY(cudaStreamSynchronize(st));
-        map_ms += elapsed(ctx->ev[4], ctx->ev[5]);
-        nuts_ms += elapsed(ctx->ev[5], ctx->ev[6]);
-        ppc_ms += elapsed(ctx->ev[6], ctx->ev[7]);
-        asm_ms += elapsed(ctx->ev[7], ctx->ev[8]);
+        // ---- this chunk's results back to the caller's host buffers ----
+        if (host) {
+            const size_t o = (size_t)c0, n_ = (size_t)nc;
+            MDG_CUDA_TRY(cudaMemcpyAsync(out + o, d_out + o, n_ * sizeof(mdg_fit_result), cudaMemcpyDeviceToHost, ls));
+            if (out_median) MDG_CUDA_TRY(cudaMemcpyAsync(out_median + o * R, d_med + o * R, n_ * R * 4, cudaMemcpyDeviceToHost, ls));
+            if (out_hpdi_lo) MDG_CUDA_TRY(cudaMemcpyAsync(out_hpdi_lo + o * R, d_lo + o * R, n_ * R * 4, cudaMemcpyDeviceToHost, ls));
+            if (out_hpdi_hi) MDG_CUDA_TRY(cudaMemcpyAsync(out_hpdi_hi + o * R, d_hi + o * R, n_ * R * 4, cudaMemcpyDeviceToHost, ls));
+            const size_t so = o * MDG_NUM_RUNS * S * 4, to = o * MDG_NUM_RUNS * (size_t)(W + S) * 4, wo = o * MDG_NUM_RUNS * 2 * R;
+            if (out_samples) MDG_CUDA_TRY(cudaMemcpyAsync(out_samples + so, d_samples + so, n_ * MDG_NUM_RUNS * S * 4 * 8, cudaMemcpyDeviceToHost, ls));
+            if (out_trace) MDG_CUDA_TRY(cudaMemcpyAsync(out_trace + to, d_trace + to, n_ * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8, cudaMemcpyDeviceToHost, ls));
+            if (out_waic) MDG_CUDA_TRY(cudaMemcpyAsync(out_waic + wo, d_waic_user + wo, n_ * MDG_NUM_RUNS * 2 * R * 8, cudaMemcpyDeviceToHost, ls));
+        }
+        MDG_CUDA_TRY(cudaMemcpyAsync(ln.h_leap, d_leap, MDG_NUM_RUNS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ls));
+        MDG_CUDA_TRY(cudaEventRecord(ln.ev[4], ls));
+        ln.launches = ctx->timings.n_launches - launches_before;
+        ln.busy = true;
+        ln.owner = slot;
     }
-
-    if (host) {
-        MDG_CUDA_TRY(cudaMemcpyAsync(out, d_out, nt * sizeof(mdg_fit_result), cudaMemcpyDeviceToHost, st));
-        if (out_median) MDG_CUDA_TRY(cudaMemcpyAsync(out_median, d_med, nt * R * 4, cudaMemcpyDeviceToHost, st));
-        if (out_hpdi_lo) MDG_CUDA_TRY(cudaMemcpyAsync(out_hpdi_lo, d_lo, nt * R * 4, cudaMemcpyDeviceToHost, st));
-        if (out_hpdi_hi) MDG_CUDA_TRY(cudaMemcpyAsync(out_hpdi_hi, d_hi, nt * R * 4, cudaMemcpyDeviceToHost, st));
-        if (out_samples) MDG_CUDA_TRY(cudaMemcpyAsync(out_samples, d_samples, nt * MDG_NUM_RUNS * S * 4 * 8, cudaMemcpyDeviceToHost, st));
-        if (out_trace) MDG_CUDA_TRY(cudaMemcpyAsync(out_trace, d_trace, nt * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8, cudaMemcpyDeviceToHost, st));
-        if (out_waic) MDG_CUDA_TRY(cudaMemcpyAsync(out_waic, d_waic_user, nt * MDG_NUM_RUNS * 2 * R * 8, cudaMemcpyDeviceToHost, st));
-    }
-    unsigned long long h_leap[MDG_NUM_RUNS] = {};
-    MDG_CUDA_TRY(cudaMemcpyAsync(h_leap, d_leap, sizeof h_leap, cudaMemcpyDeviceToHost, st));
-    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[9], st));
-    MDG_CUDA_TRY(cudaStreamSynchronize(st));
-    ctx->timings.map_ms = map_ms;
-    ctx->timings.nuts_ms = nuts_ms;
-    ctx->timings.ppc_ms = ppc_ms;
-    ctx->timings.assemble_ms = asm_ms;
-    ctx->timings.total_ms = elapsed(ctx->ev[0], ctx->ev[9]);
-    for (int r = 0; r < MDG_NUM_RUNS; ++r) ctx->timings.leapfrogs[r] = h_leap[r];
     return MDG_OK;
+}
+
+int mdg_fit_batch_wait(mdg_ctx* ctx, int64_t ticket, mdg_timings* out_timings) {
+    if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
+    int slot = -1;
+    for (int i = 0; i < kFitTickets; ++i) if (ctx->ticket[i].active && ctx->ticket[i].id == ticket) slot = i;
+    if (slot < 0) { set_error("mdg_fit_batch_wait: unknown ticket %lld", (long long)ticket); return MDG_ERR_INVALID; }
+    DeviceGuard guard(ctx->device);
+    mdg_fit_ticket_slot& tk = ctx->ticket[slot];
+    // harvest this ticket's chunks in submission order: the lane after `next_lane - 1` is the older one
+    for (int i = 0; i < kFitLanes; ++i) {
+        mdg_fit_lane& ln = ctx->lane[(ctx->next_lane + i) % kFitLanes];
+        if (ln.busy && ln.owner == slot) {
+            // later work on the ctx stream (e.g. the caller's consumers of device-resident results) follows the chunk
+            MDG_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ln.ev[4], 0));
+            int rc = harvest_lane(ctx, ln);
+            if (rc) return rc;
+        }
+    }
+    tk.t.nuts_begin_ms = (float)tk.nuts_begin_ms;
+    tk.t.nuts_end_ms = (float)tk.nuts_end_ms;
+    tk.active = false;
+    ctx->timings = tk.t;
+    if (out_timings) *out_timings = tk.t;
+    return MDG_OK;
+}
+
+int mdg_fit_batch(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position, const int64_t* tax_id, const uint32_t* k,
+                  const uint32_t* N, const uint32_t* mism12, const double* noise3, const mdg_fit_config* cfg,
+                  mdg_fit_result* out, float* out_median, float* out_hpdi_lo, float* out_hpdi_hi,
+                  double* out_samples, double* out_trace, double* out_waic) {
+    int64_t ticket = 0;
+    int rc = mdg_fit_batch_submit(ctx, mem, n_tax, max_position, tax_id, k, N, mism12, noise3, cfg, out, out_median, out_hpdi_lo,
+                                  out_hpdi_hi, out_samples, out_trace, out_waic, &ticket);
+    if (rc) return rc;
+    return mdg_fit_batch_wait(ctx, ticket, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
     log_table_init();
     prior_table_init<MODEL>(sh_prior, p.pr, 1);
     const double phi_min = p.pr.phi_min;
+    const uint32_t budget = p.cfg.max_leapfrogs_per_run > 0 ? (uint32_t)p.cfg.max_leapfrogs_per_run : 0u;
 
     for (;;) {
         if (lane == 0) sh_item[warp] = atomicAdd(p.work_counter, 1u);
@@ -348,6 +349,8 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                 for (int j = 0; j < D; ++j) { zn[j] = sh.zn_park[j]; rh[j] = sh.rh_park[j]; }
 #endif
                 ++n_grad;
+                // bounded work per run: the analogue of the reference's per-fit timeout (fits.py:472-474)
+                if (budget != 0u && n_grad > budget) { failed = 2; break; }
                 pen = valid ? -logp : nan("");
 #pragma unroll
                 for (int j = 0; j < D; ++j) { gn[j] = valid ? -grad[j] : nan(""); rn[j] = fma(-0.5 * e, gn[j], rh[j]); }
@@ -437,6 +440,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                                 if (take_main) { sh.zp[j] = sh.szp[j]; sh.gp[j] = sh.sgp[j]; }
                             }
                         }
+                        __syncwarp(gmask);  // lane 0 is back before anybody touches group-uniform state again
 #pragma unroll
                         for (int j = 0; j < D; ++j) m_rsum[j] += s_rsum[j];
                         __syncwarp(gmask);
@@ -491,8 +495,10 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                                             sh.wf_m2[j] += dpre * (zc[j] - mn);
                                         }
                                     }
+                                    __syncwarp(gmask);
                                 }
                                 const bool at_end = (t == p.win_end[window_idx]);
+                                __syncwarp(gmask);  // every lane has read window_idx before it moves
                                 if (at_end) window_idx += 1;
                                 if (at_end && is_middle) {
                                     __syncwarp(gmask);
@@ -506,6 +512,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
 #pragma unroll
                                         for (int j = 0; j < D; ++j) { sh.wf_mean[j] = 0.0; sh.wf_m2[j] = 0.0; }
                                     }
+                                    __syncwarp(gmask);
                                     wf_n = 0;
                                     want_heur = p.cfg.find_heuristic_step_size != 0;
                                     if (!want_heur) reset_dual_averaging();
@@ -532,6 +539,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
                                         dst[0] = th[0]; dst[1] = th[1]; dst[2] = th[2]; dst[3] = th[3];
                                     }
                                 }
+                                __syncwarp(gmask);
                                 // WAIC: streaming logsumexp + Welford of this lane's log-likelihood (fits.py:147-165)
 #pragma unroll
                                 for (int s = 0; s < NPL; ++s) {
@@ -549,6 +557,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_kernel(co
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) dst[j] = j < D ? zc[j] : nan("");
                             }
+                            __syncwarp(gmask);
                             t += 1;
                             if (t >= W + S) break;
                             bool heur_running = false;

@@ -288,6 +288,7 @@ __global__ void assemble_kernel(const AssembleLaunch p) {
         r.run[i].waic = rr[i].waic;
         r.run[i].lppd = rr[i].lppd;
         if (rr[i].failed) status |= MDG_FIT_FAILED;
+        if (rr[i].failed == 2u) status |= MDG_FIT_BUDGET_EXCEEDED;
         if (rr[i].n_divergent) status |= MDG_FIT_HAS_DIVERGENCES;
         atomicAdd(&p.leapfrog_totals[i], (unsigned long long)rr[i].n_leapfrog);
     }

@@ -38,7 +38,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_version_and_default_config(lib):
     from metadamage_b200 import _lib
 
-    assert lib.mdg_version() == 100
+    assert lib.mdg_version() == 200
     cfg = _lib.default_config()
     # fits.py:792-799 and the priors of fits.py:43-67
     assert (cfg.num_warmup, cfg.num_samples, cfg.max_tree_depth) == (500, 1000, 10)

@@ -144,3 +144,24 @@ def test_counts_full_size_properties(ctx):
     r2 = ctx.counts_reduce(g["tax_id"], g["n_alignments"], g["is_reverse"], g["pos0"], g["counts16"])
     for key in ROW_KEYS + TAX_KEYS + ("f_fwd", "f_rev"):
         assert r[key].tobytes() == r2[key].tobytes()
+
+
+def test_counts_full_size_bit_exact_vs_oracle(ctx, oracle):
+    """BASELINE config 5 at full size (10M rows, 333 334 TaxIDs): EVERY output of K1 — the per-row
+    columns n_fwd_ref, n_rev_ref, f_fwd, f_rev (float32 bit patterns), z, y_sum_total, keep and the
+    per-TaxID tax_id, n_alignments, first_row, dense k/N, noise — against the oracle's restatement of
+    counts.py:237-256 on the same rows, including N = 0 rows (0/0 -> 0) and the failing TaxIDs."""
+    g = syn.make_mismatch_matrix(333_334, max_position=15, seed=syn.SEEDS["cfg5"])
+    # force some all-zero reference rows (N = 0 -> f = 0, counts.py:254) and k = 0 rows into the stress input
+    rng = np.random.default_rng(5)
+    c16 = g["counts16"].copy()
+    n = c16.shape[1]
+    c16[:, rng.integers(0, n, 50_000)] = 0
+    c16[7, rng.integers(0, n, 200_000)] = 0   # CT
+    c16[8, rng.integers(0, n, 200_000)] = 0   # GA
+    args = (g["tax_id"], g["n_alignments"], g["is_reverse"], g["pos0"], c16)
+    r = ctx.counts_reduce(*args, want_noise=True)
+    o = oracle.counts_reduce(*args)
+    assert n >= 10_000_000 and o["n_tax"] > 50_000
+    assert (o["n_fwd_ref"] == 0).sum() > 1000 and (o["keep"] == 0).sum() > 1_000_000
+    assert_same(r, o)

@@ -1,0 +1,98 @@
+"""-m gpu: the north star's MCMC parity gate at scale.
+
+BASELINE.json: "posterior D-max mean and std within 3x Monte-Carlo standard error". Here 256 TaxIDs of
+BASELINE config 2's heavy-tailed generator (the whole lowest-coverage decile region sampled densely: that
+is where chains touch the clip(Dz, 0, 1) boundary and diverge) and 64 TaxIDs of config 4 (--max-position 25,
+GA/CT) are fitted by the CUDA kernels through the C-ABI and by the oracle (CPU), both with the reference's
+500 + 1000 schedule. For every TaxID and every statistic the difference of the two estimates is divided by
+its Monte-Carlo standard error (batch means on both chains); the z-scores of a correct sampler pair are
+~ t-distributed around 0:
+
+    * at most 1 % of all z-scores beyond 3 (2 % within any single statistic),
+    * |mean z| < 0.2 for every statistic (no systematic shift of one side),
+    * n_sigma, the headline significance, inside the band the round-1 4-TaxID test used.
+
+Both settings of find_heuristic_step_size go through the same gate (0 is numpyro 0.4.1's default).
+"""
+import numpy as np
+import pytest
+
+from conftest import mcse_batch_means
+from metadamage_b200 import _lib, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def pick_taxa(n_pool, n_low, n_rest, max_position, seed, **kw):
+    """`n_low` TaxIDs evenly spread over the lowest-coverage decile of a pool of `n_pool` fitted TaxIDs and
+    `n_rest` evenly spread over the other nine deciles."""
+    tid, k, N, _ = syn.dense_fit_batch(n_pool, max_position=max_position, seed=seed, **kw)
+    order = np.argsort(N.sum(axis=1, dtype=np.int64), kind="stable")
+    dec = n_pool // 10
+    low = order[:dec][np.linspace(0, dec - 1, n_low).astype(int)]
+    rest = order[dec:][np.linspace(0, n_pool - dec - 1, n_rest).astype(int)]
+    sel = np.sort(np.concatenate([low, rest]))
+    return tid[sel], np.ascontiguousarray(k[sel]), np.ascontiguousarray(N[sel])
+
+
+def z_scores(sa, sb):
+    """z-scores (CUDA - oracle) / MCSE for the four gated statistics of one TaxID's PMD/all run;
+    sa, sb: [S][4] constrained draws (q, A, c, phi)."""
+    out = {}
+    for name, fa, fb in (("D_max_mean", sa[:, 1] + sa[:, 2], sb[:, 1] + sb[:, 2]), ("q_mean", sa[:, 0], sb[:, 0]),
+                         ("concentration_mean", sa[:, 3], sb[:, 3])):
+        se = np.hypot(mcse_batch_means(fa), mcse_batch_means(fb))
+        out[name] = (fa.mean() - fb.mean()) / max(se, 1e-300)
+    da, db = sa[:, 1] + sa[:, 2], sb[:, 1] + sb[:, 2]
+    va, vb = (da - da.mean()) ** 2, (db - db.mean()) ** 2
+    se = np.hypot(mcse_batch_means(va), mcse_batch_means(vb))
+    out["D_max_std"] = (va.mean() - vb.mean()) / max(se, 1e-300)
+    return out
+
+
+def run_gate(ctx, oracle, tid, k, N, heuristic, label):
+    kw = dict(find_heuristic_step_size=heuristic)
+    got = ctx.fit_batch(tid, k, N, _lib.default_config(**kw), want_samples=True)
+    exp = oracle.fit_batch(tid, k, N, oracle.default_config(**kw), want_samples=True)
+    res, ref = got["result"], exp["result"]
+    assert ((res["status"] | ref["status"]) & 1).sum() == 0, "a fit failed"
+    zs = {}
+    for i in range(len(tid)):
+        for name, z in z_scores(got["samples"][i, 0], exp["samples"][i, 0]).items():
+            zs.setdefault(name, []).append(z)
+    summary = {name: (float(np.mean(v)), float(np.mean(np.abs(v) > 3.0)), float(np.std(v))) for name, v in zs.items()}
+    allz = np.concatenate([np.asarray(v) for v in zs.values()])
+    msg = f"{label}: (mean z, share beyond 3, sd z) = {summary}; pooled share beyond 3 = {np.mean(np.abs(allz) > 3):.4f}"
+    print(msg)
+    assert np.mean(np.abs(allz) > 3.0) <= 0.01, msg
+    for name, (mz, share, sd) in summary.items():
+        assert share <= 0.02, msg
+        assert abs(mz) < 0.2, msg
+        assert 0.7 < sd < 1.45, msg   # the spread of z is that of unit-variance noise: the MCSEs are honest
+    # the fields of the result row are the statistics of those same draws
+    sa = got["samples"][:, 0]
+    assert np.allclose(res["D_max_marginalized_mean"], (sa[:, :, 1] + sa[:, :, 2]).mean(axis=1), rtol=0, atol=1e-10)
+    assert np.allclose(res["q_mean"], sa[:, :, 0].mean(axis=1), rtol=0, atol=1e-10)
+    # n_sigma: a noisy function of 2 x 1000 draws on both sides
+    band = 0.35 * (1 + np.abs(ref["n_sigma"]))
+    inside = np.abs(res["n_sigma"] - ref["n_sigma"]) < band
+    assert inside.mean() >= 0.97, f"{label}: n_sigma outside the band for {np.flatnonzero(~inside)}"
+    # sampler efficiency must agree as well: same algorithm, same adaptation
+    la, lb = res["run"]["n_leapfrog"].astype(float), ref["run"]["n_leapfrog"].astype(float)
+    assert abs(np.log(la.sum(axis=0) / lb.sum(axis=0))).max() < 0.1, (la.sum(axis=0), lb.sum(axis=0))
+    return got, exp
+
+
+@pytest.mark.parametrize("heuristic", [0, 1])
+def test_cfg2_parity_gate_256_taxa(ctx, oracle, heuristic):
+    tid, k, N = pick_taxa(2560, 64, 192, 15, syn.SEEDS["cfg2"])
+    assert len(np.unique(tid)) == 256
+    run_gate(ctx, oracle, tid, k, N, heuristic, f"cfg2 heuristic={heuristic}")
+
+
+def test_cfg4_parity_gate_64_taxa(ctx, oracle):
+    """BASELINE config 4: --max-position 25, --substitution-bases-forward GA --substitution-bases-reverse CT
+    (two positions per lane in the kernels)."""
+    tid, k, N = pick_taxa(640, 16, 48, 25, syn.SEEDS["cfg4"], fwd="GA", rev="CT")
+    got, _ = run_gate(ctx, oracle, tid, k, N, 0, "cfg4 P=25 GA/CT")
+    assert np.median(got["result"]["n_sigma"]) < 2.0   # the control run sees no damage
