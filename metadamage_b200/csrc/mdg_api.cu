@@ -11,6 +11,7 @@
 #include "mdg_tsv_kernel.cuh"
 #include "mdg_select_kernel.cuh"
 #include "mdg_post_kernels.cuh"
+#include "mdg_nuts_kernel.cuh"
 
 namespace mdg {
 
@@ -61,7 +62,7 @@ struct mdg_fit_lane {
     cudaStream_t main = nullptr, side[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[5] = {};  // chunk begin, MAP end, NUTS end, predictive end, done (after assembly + D2H)
     cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
-    mdg::DevBuf rec, map, pred, counters, samples, waic;
+    mdg::DevBuf rec, map, pred, counters, samples, waic, waic_acc[4];
     unsigned long long* h_leap = nullptr;  // pinned [MDG_NUM_RUNS]
     bool busy = false;
     int owner = -1;          // ticket slot of the chunk in flight
@@ -194,6 +195,36 @@ int launch_nuts_dispatch(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl, int
     if (npl == 1) return launch_nuts<MODEL, 1, 32>(ctx, st, fl);
     if (npl == 2) return launch_nuts<MODEL, 2, 32>(ctx, st, fl);
     return launch_nuts<MODEL, 4, 32>(ctx, st, fl);
+}
+
+// K4, group layout: GW lanes per chain, rolled position loop (mdg_nuts_kernel.cuh)
+template <int MODEL, int GW>
+int launch_nuts_group(mdg_ctx* ctx, cudaStream_t st, FitLaunch fl, DevBuf& acc) {
+    auto kern = nuts_group_kernel<MODEL, GW, kNutsWarps>;
+    int n_obs = 0;
+    for (int m = fl.mask0; m < fl.mask0 + fl.n_masks; ++m) n_obs = std::max(n_obs, m == 0 ? 2 * fl.P : fl.P);
+    fl.n_slots = (n_obs + 1 + GW - 1) / GW;  // index 0 is the spare
+    const size_t smem = (size_t)kNutsWarps * nuts_warp_smem_bytes(fl.n_slots);
+    MDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = persistent_grid(kern, kNutsWarps * 32, smem, ctx->num_sms, fl.n_items, kNutsWarps * (32 / GW));
+    int rc = acc.ensure((size_t)grid * kNutsWarps * 4 * fl.n_slots * 32 * sizeof(double));
+    if (rc) return rc;
+    fl.waic_acc = acc.as<double>();
+    kern<<<grid, kNutsWarps * 32, smem, st>>>(fl);
+    MDG_CUDA_TRY(cudaGetLastError());
+    ctx->timings.n_launches++;
+    return MDG_OK;
+}
+
+template <int MODEL>
+int launch_nuts_group_dispatch(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl, DevBuf& acc, int gw) {
+    if (gw == 16) return launch_nuts_group<MODEL, 16>(ctx, st, fl, acc);
+    return launch_nuts_group<MODEL, 8>(ctx, st, fl, acc);
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 int launch_map(mdg_ctx* ctx, cudaStream_t st, const MapLaunch& ml, int npl) {
@@ -331,7 +362,9 @@ void mdg_ctx_destroy(mdg_ctx* ctx) {
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
     if (ctx->inputs_ready) cudaEventDestroy(ctx->inputs_ready);
     for (auto& ln : ctx->lane) {
-        for (mdg::DevBuf* b : {&ln.rec, &ln.map, &ln.pred, &ln.counters, &ln.samples, &ln.waic}) b->release();
+        for (mdg::DevBuf* b : {&ln.rec, &ln.map, &ln.pred, &ln.counters, &ln.samples, &ln.waic, &ln.waic_acc[0], &ln.waic_acc[1],
+                               &ln.waic_acc[2], &ln.waic_acc[3]})
+            b->release();
         for (int i = 0; i < 5; ++i) if (ln.ev[i]) cudaEventDestroy(ln.ev[i]);
         if (ln.fork_ev) cudaEventDestroy(ln.fork_ev);
         for (int i = 0; i < 3; ++i) {
@@ -1015,16 +1048,25 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
             b.n_masks = 1; b.mask0 = 0; b.n_items = nc; b.work_counter = d_counters + 2;
             FitLaunch c = fl, d = fl;  // PMD / null, forward-only and reverse-only
             c.work_counter = d_counters + 3; d.work_counter = d_counters + 4;
-            if (pack) {
+            const bool v1 = env_int("MDG_NUTS_V1", 0) != 0;  // round-1 kernel (one chain per warp / half warp), kept for A/B runs
+            if (v1 && pack) {
                 c.n_items = nc; d.n_items = nc; c.n_masks = 1; d.n_masks = 1; c.mask0 = 1; d.mask0 = 1;
             } else {
                 c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_masks = 2; d.n_masks = 2; c.mask0 = 1; d.mask0 = 1;
             }
-            const int npl_half = pack ? 1 : npl_for(P, 32), gw_half = pack ? 16 : 32;
-            if (fwd_rev && (rc = launch_nuts_dispatch<0>(ctx, ln.side[1], c, npl_half, gw_half))) return bail(rc);
-            if ((rc = launch_nuts_dispatch<0>(ctx, ls, a, npl_for(R, 32), 32))) return bail(rc);
-            if (fwd_rev && (rc = launch_nuts_dispatch<1>(ctx, ln.side[2], d, npl_half, gw_half))) return bail(rc);
-            if ((rc = launch_nuts_dispatch<1>(ctx, ln.side[0], b, npl_for(R, 32), 32))) return bail(rc);
+            if (v1) {
+                const int npl_half = pack ? 1 : npl_for(P, 32), gw_half = pack ? 16 : 32;
+                if (fwd_rev && (rc = launch_nuts_dispatch<0>(ctx, ln.side[1], c, npl_half, gw_half))) return bail(rc);
+                if ((rc = launch_nuts_dispatch<0>(ctx, ls, a, npl_for(R, 32), 32))) return bail(rc);
+                if (fwd_rev && (rc = launch_nuts_dispatch<1>(ctx, ln.side[2], d, npl_half, gw_half))) return bail(rc);
+                if ((rc = launch_nuts_dispatch<1>(ctx, ln.side[0], b, npl_for(R, 32), 32))) return bail(rc);
+            } else {
+                const int gw_all = env_int("MDG_GW_ALL", 8), gw_half = env_int("MDG_GW_HALF", 8);
+                if (fwd_rev && (rc = launch_nuts_group_dispatch<0>(ctx, ln.side[1], c, ln.waic_acc[2], gw_half))) return bail(rc);
+                if ((rc = launch_nuts_group_dispatch<0>(ctx, ls, a, ln.waic_acc[0], gw_all))) return bail(rc);
+                if (fwd_rev && (rc = launch_nuts_group_dispatch<1>(ctx, ln.side[2], d, ln.waic_acc[3], gw_half))) return bail(rc);
+                if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
+            }
         }
         for (int i = 0; i < 3; ++i) {
             MDG_CUDA_TRY(cudaEventRecord(ln.join_ev[i], ln.side[i]));

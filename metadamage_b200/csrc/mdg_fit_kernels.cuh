@@ -48,6 +48,8 @@ struct FitLaunch {
     int sample_slot[MDG_NUM_RUNS];  // run kind -> slot in `samples`, -1 = not stored
     int sample_runs;
     double* trace;      // [n_tax][6][W+S][4] or NULL
+    int n_slots;        // group kernel: rounds of the position loop, ceil((n_obs + 1) / GW)
+    double* waic_acc;   // group kernel: WAIC accumulators, [grid * warps][4][n_slots][32]
 };
 
 template <int D>

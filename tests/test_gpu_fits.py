@@ -394,73 +394,12 @@ def test_leapfrog_budget_is_the_timeout_analogue(ctx, oracle):
     assert np.all(np.isnan(lim["D_max"][over])) and np.all(np.isnan(lim["n_sigma"][over]))
     # no run of a flagged TaxID went past the budget by more than the trip that noticed it
     assert lim["run"]["n_leapfrog"].max() <= budget + 1
+    # the oracle applies the same rule to its own chains (they coincide with the kernel's only until round-off
+    # amplifies, so run lengths differ between the two; each side is checked against its own unlimited run)
+    exp_free = oracle.fit_batch(tid, k, N, oracle.default_config(**kw))["result"]
     exp = oracle.fit_batch(tid, k, N, oracle.default_config(max_leapfrogs_per_run=budget, **kw))["result"]
-    flagged_o = (exp["status"] & FIT_BUDGET_EXCEEDED) != 0
-    # chains coincide only until round-off amplifies, so a run whose length sits right at the budget may differ
-    near = np.abs(longest.astype(float) - budget) < 0.02 * budget
-    assert np.array_equal(flagged_o[~near], over[~near])
-
-
-def test_async_submit_wait_overlaps_batches_bit_identically(ctx):
-    """mdg_fit_batch_submit / _wait: two batches in flight on one ctx (separate lanes, streams, scratch) give the
-    rows of two synchronous calls, bit for bit; a third submit is refused with MDG_ERR_BUSY; chunks of one batch
-    alternate between the lanes the same way."""
-    from metadamage_b200._lib import MdgError
-
-    tid, k, N = small_batch(60, seed=81)
-    cfg = _lib.default_config(num_warmup=80, num_samples=90)
-    a_sync = ctx.fit_batch(tid[:33], k[:33], N[:33], cfg)
-    b_sync = ctx.fit_batch(tid[33:], k[33:], N[33:], cfg)
-    ta = ctx.fit_submit(tid[:33], k[:33], N[:33], cfg)
-    tb = ctx.fit_submit(tid[33:], k[33:], N[33:], cfg)
-    with pytest.raises(MdgError, match="in flight"):
-        ctx.fit_submit(tid[:5], k[:5], N[:5], cfg)
-    a = ctx.fit_wait(ta)
-    b = ctx.fit_wait(tb)
-    assert a["result"].tobytes() == a_sync["result"].tobytes() and b["result"].tobytes() == b_sync["result"].tobytes()
-    assert a["median"].tobytes() == a_sync["median"].tobytes() and b["hpdi_hi"].tobytes() == b_sync["hpdi_hi"].tobytes()
-    # timings: per-batch spans overlap, the union does not double count
-    ta_, tb_ = a["timings"], b["timings"]
-    assert ta_["nuts_ms"] > 0 and tb_["nuts_ms"] > 0
-    assert sum(ta_["leapfrogs"]) == int(a["result"]["run"]["n_leapfrog"].sum())
-    assert ta_["nuts_union_ms"] + tb_["nuts_union_ms"] <= (max(ta_["nuts_end_ms"], tb_["nuts_end_ms"]) - min(ta_["nuts_begin_ms"], tb_["nuts_begin_ms"])) * 1.001 + 0.01
-    assert tb_["nuts_begin_ms"] < ta_["nuts_end_ms"], "the second batch did not start under the first one's tail"
-    # a ticket can only be waited for once
-    with pytest.raises(MdgError, match="unknown ticket"):
-        ctx.fit_wait(dict(ta))
-    # many chunks of one batch while another batch is in flight
-    os.environ["MDG_FIT_CHUNK"] = "9"
-    try:
-        t1 = ctx.fit_submit(tid, k, N, cfg)
-        t2 = ctx.fit_submit(tid[::-1].copy(), k[::-1].copy(), N[::-1].copy(), cfg)
-        r1, r2 = ctx.fit_wait(t1), ctx.fit_wait(t2)
-    finally:
-        del os.environ["MDG_FIT_CHUNK"]
-    both = np.concatenate([a_sync["result"], b_sync["result"]])
-    assert r1["result"].tobytes() == both.tobytes() and r2["result"].tobytes() == both[::-1].tobytes()
-
-
-def test_async_device_resident_pipeline(ctx):
-    """The bench's pipelined loop: counts on the ctx stream, fits submitted on device buffers, two in flight."""
-    import torch
-
-    from metadamage_b200._abi import FIT_RESULT_DTYPE
-
-    dev = torch.device("cuda", 0)
-    cfg = _lib.default_config(num_warmup=60, num_samples=64)
-    batches = [small_batch(24, seed=90 + i) for i in range(3)]
-    want = [ctx.fit_batch(*b, cfg)["result"] for b in batches]
-    bufs, tickets, got = [], [], []
-    for tid, k, N in batches:
-        d = dict(tid=torch.from_numpy(tid).to(dev), k=torch.from_numpy(k.view(np.int32)).to(dev), N=torch.from_numpy(N.view(np.int32)).to(dev),
-                 out=torch.zeros(len(tid) * FIT_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev))
-        bufs.append(d)
-        tickets.append(ctx.fit_submit_device(d["tid"], d["k"], d["N"], d["out"], cfg))
-        if len(tickets) == 2:
-            ctx.fit_wait(tickets.pop(0))
-            got.append(bufs[len(got)]["out"].cpu().numpy().view(FIT_RESULT_DTYPE))
-    while tickets:
-        ctx.fit_wait(tickets.pop(0))
-        got.append(bufs[len(got)]["out"].cpu().numpy().view(FIT_RESULT_DTYPE))
-    for g_, w_ in zip(got, want):
-        assert g_.tobytes() == w_.tobytes()
+    over_o = exp_free["run"]["n_leapfrog"].max(axis=1) > budget
+    assert np.array_equal((exp["status"] & FIT_BUDGET_EXCEEDED) != 0, over_o)
+    assert np.array_equal((exp["status"] & FIT_FAILED) != 0, over_o)
+    assert exp[~over_o].tobytes() == exp_free[~over_o].tobytes()
+    assert abs(int(over_o.sum()) - int(over.sum())) <= 8

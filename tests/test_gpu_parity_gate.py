@@ -68,7 +68,8 @@ def run_gate(ctx, oracle, tid, k, N, heuristic, label):
     for name, (mz, share, sd) in summary.items():
         assert share <= 0.02, msg
         assert abs(mz) < 0.2, msg
-        assert 0.7 < sd < 1.45, msg   # the spread of z is that of unit-variance noise: the MCSEs are honest
+        assert 0.4 < sd < 1.45, msg   # not wider than unit-variance noise (narrower is expected: both sides draw from the
+        #                             same Philox streams, so the two chains start out identical and stay correlated)
     # the fields of the result row are the statistics of those same draws
     sa = got["samples"][:, 0]
     assert np.allclose(res["D_max_marginalized_mean"], (sa[:, :, 1] + sa[:, :, 2]).mean(axis=1), rtol=0, atol=1e-10)
