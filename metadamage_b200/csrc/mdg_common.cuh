@@ -227,9 +227,16 @@ __device__ __forceinline__ void normal2(uint4 o, double& n0, double& n1) {
 // transition or rarer). The NUTS kernel was instruction-fetch bound (ncu: stall_no_instruction
 // 45 % of all stalls with 12.4k SASS instructions); one shared copy of each keeps the hot loop
 // (one gradient evaluation + leaf bookkeeping) inside the instruction caches.
-__device__ MDG_COLD double exp_cold(double x) { return exp(x); }
-__device__ MDG_COLD double log_cold(double x) { return log(x); }
-__device__ MDG_COLD double sigmoid_cold(double x) { return 1.0 / (1.0 + exp(-x)); }
+// They use the kernels' own table-driven exp / log (a few ulp; the CUDA library versions are 2-4x as many
+// instructions and every one of them is issued for ONE chain): the library call only backs up arguments
+// outside the fast paths' domain.
+__device__ MDG_COLD double exp_cold(double x) { return exp_fast(x); }
+__device__ MDG_COLD double log_cold(double x) { return (x >= 2.2250738585072014e-308 && x < INFINITY) ? log_pos(x) : log(x); }
+__device__ MDG_COLD double sigmoid_cold(double x) {
+    const double e = exp_fast(-fabs(x));  // in (0, 1]
+    const double inv = rcp_pos(1.0 + e);
+    return x != x ? x : (x >= 0.0 ? inv : e * inv);
+}
 
 // st = lgamma(y) - 0.5 log(2 pi) and dg = digamma(y) for y >= 10, t = 1/y (5 Bernoulli terms each)
 __device__ __forceinline__ double log_sel(double x) {

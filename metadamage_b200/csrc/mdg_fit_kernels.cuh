@@ -72,6 +72,7 @@ struct GroupShared {
     // parked here so that the evaluation's five interleaved special-function chains get the registers
     double imm[D], s_rsum[D], zn_park[D], rh_park[D], E0, s_weight, s_sum_acc;
 #endif
+    double isd[D];  // group kernel: 1 / sqrt(imm) = sqrt of the mass matrix diagonal (momentum r ~ N(0, M) is n * isd)
     int da_t, wf_n, window_idx, h_last, h_dir, m_nprop;
     uint32_t h_att, h_call, init_attempt, n_div;
 };

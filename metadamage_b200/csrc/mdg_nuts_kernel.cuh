@@ -31,6 +31,29 @@
 
 namespace mdg {
 
+// momentum r ~ N(0, M), M^-1 = diag(imm): r_j = n_j * isd_j with isd = 1 / sqrt(imm) kept per chain (it changes at
+// the four adaptation-window ends only); Philox + Box-Muller out of line
+template <int D>
+__device__ MDG_COLD Vec4 draw_normals_cold(uint2 key, uint32_t c1, uint32_t c2, uint32_t c3) {
+    Vec4 r;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        double n0 = 0.0, n1 = 0.0;
+        if (2 * b < D) normal2(philox4x32(key, (uint32_t)b, c1, c2, c3), n0, n1);
+        r.v[2 * b] = n0;
+        r.v[2 * b + 1] = n1;
+    }
+    return r;
+}
+
+template <int D>
+__device__ __forceinline__ void draw_momentum_scaled(uint2 key, uint32_t c1, uint32_t c2, uint32_t c3, const double (&isd)[D],
+                                                     double (&r)[D]) {
+    const Vec4 n = draw_normals_cold<D>(key, c1, c2, c3);
+#pragma unroll
+    for (int j = 0; j < D; ++j) r[j] = n.v[j] * isd[j];
+}
+
 enum GroupPhase : int { GP_FETCH = 0, GP_INIT = 1, GP_HEUR = 2, GP_LEAF = 3, GP_IDLE = 4 };
 
 // bytes of dynamic shared memory per warp: {k, N} as doubles + four log-likelihood buffers, [n_slots][32] each
@@ -259,7 +282,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
     // begin a transition from the chain state held in sh.zp / sh.gp / pe_cur
     auto start_transition = [&]() {
         double r0[D];
-        draw_momentum<D>(key, (uint32_t)t, c2word(run_kind, P_MOM), 0u, imm, r0);
+        draw_momentum_scaled<D>(key, (uint32_t)t, c2word(run_kind, P_MOM), 0u, sh.isd, r0);
         E0 = pe_cur + kinetic<D>(imm, r0);
         __syncwarp(gmask);
         if (lig == 0) {
@@ -285,7 +308,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
         bool large_ok = (h_step < 1.7976931348623157e308) || (h_dir <= 0);
         if (!(small_ok && large_ok && (h_last == 0 || h_dir == h_last))) return false;
         h_step *= (h_dir > 0 ? 2.0 : (h_dir < 0 ? 0.5 : 1.0));
-        draw_momentum<D>(key, h_call, c2word(run_kind, P_HEUR), h_att, imm, rf);
+        draw_momentum_scaled<D>(key, h_call, c2word(run_kind, P_HEUR), h_att, sh.isd, rf);
         ++h_att;
         h_Er = kinetic<D>(imm, rf) + pe_cur;
         __syncwarp(gmask);
@@ -335,7 +358,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
                 s_nprop = 0; s_div = false; leaf_counter = 0; t = 0;
                 __syncwarp(gmask);
 #pragma unroll
-                for (int j = 0; j < D; ++j) imm[j] = 1.0;
+                for (int j = 0; j < D; ++j) { imm[j] = 1.0; sh.isd[j] = 1.0; }
                 E0 = 0.0; s_weight = 0.0; s_sum_acc = 0.0;
                 eps = p.cfg.init_step_size; pe_cur = 0.0;
                 da_x = 0.0; da_xavg = 0.0; da_gavg = 0.0; da_prox = 0.0; da_t = 0; wf_n = 0; window_idx = 0;
@@ -530,7 +553,9 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
 #pragma unroll
                                 for (int j = 0; j < D; ++j) {
                                     double cov = sh.wf_m2[j] / (wf_n - 1);
-                                    imm[j] = ((double)wf_n / (wf_n + 5.0)) * cov + 1e-3 * (5.0 / (wf_n + 5.0));
+                                    const double v = ((double)wf_n / (wf_n + 5.0)) * cov + 1e-3 * (5.0 / (wf_n + 5.0));
+                                    imm[j] = v;
+                                    sh.isd[j] = 1.0 / sqrt(v);
                                 }
                                 __syncwarp(gmask);
                                 if (lig == 0) {

@@ -31,12 +31,16 @@ def _draw_taxa(rng, n_tax, P):
 
 
 def make_mismatch_matrix(n_tax, max_position=15, seed=SEEDS["cfg2"], n_fit=None, min_alignments=10,
-                         min_y_sum=10, fwd="CT", rev="GA", tax_id_start=1):
+                         min_y_sum=10, fwd="CT", rev="GA", tax_id_start=1, jump=0):
     """Returns a dict with the SoA input columns, the dense k/N truth and the generator's
     parameters. If `n_fit` is given, `n_tax` is ignored and TaxIDs are generated until exactly
-    `n_fit` of them pass the cuts (the failing ones stay in the input)."""
+    `n_fit` of them pass the cuts (the failing ones stay in the input). `jump` selects the jump-th
+    2^128-draw block of the seed's Philox stream: the shares of one seeded data set (BASELINE config 3:
+    seed 20240002 partitioned by TaxID range over the GPUs) are generated independently, rank r with
+    jump = r, without any rank generating the others' TaxIDs."""
     P = int(max_position)
-    rng = np.random.Generator(np.random.Philox(seed))
+    bitgen = np.random.Philox(seed)
+    rng = np.random.Generator(bitgen.jumped(int(jump)) if jump else bitgen)
     bases = "ACGT"
     fr, fo = bases.index(fwd[0]), bases.index(fwd[1])
     rr, ro = bases.index(rev[0]), bases.index(rev[1])
@@ -123,6 +127,31 @@ def make_mismatch_matrix(n_tax, max_position=15, seed=SEEDS["cfg2"], n_fit=None,
         k=k_dense, N=N_dense, truth=dict(A=g["A"], q=g["q"], c=g["c"], phi=g["phi"]),
         max_position=P,
     )
+
+
+def write_tsv(g, path, legacy=False, tax_name="synthetic taxon", tax_rank="species"):
+    """Write the SoA columns of `make_mismatch_matrix` as the mismatch-matrix text file the reference parses
+    (counts.py:37-45, 229-235: 22 tab-separated columns, no header; `legacy`: the 20-column layout with a header
+    that data/input/*.txt use). pyarrow's multi-threaded CSV writer: ~1 s per million rows."""
+    import pyarrow as pa
+    import pyarrow.csv as pacsv
+
+    n = len(g["tax_id"])
+    cols = {"tax_id": pa.array(g["tax_id"])}
+    if not legacy:
+        cols["tax_name"] = pa.repeat(tax_name, n)
+        cols["tax_rank"] = pa.repeat(tax_rank, n)
+    cols["N_alignments"] = pa.array(g["n_alignments"])
+    cols["strand"] = pa.array(np.where(g["is_reverse"] == 1, "3'", "5'"))
+    cols["position"] = pa.array(g["pos0"])
+    for i, r in enumerate("ACGT"):
+        for j, o in enumerate("ACGT"):
+            cols[r + o] = pa.array(g["counts16"][4 * i + j])
+    with open(path, "wb") as fh:
+        if legacy:
+            fh.write(("\t".join(["#taxid", "Nalignments", "Direction", "Pos"] + list(cols)[4:]) + "\n").encode())
+        pacsv.write_csv(pa.table(cols), fh, write_options=pacsv.WriteOptions(include_header=False, delimiter="\t", quoting_style="none"))
+    return path
 
 
 def dense_fit_batch(n_fit, max_position=15, seed=SEEDS["cfg2"], **kw):
