@@ -4,23 +4,32 @@
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...        # the CPU arm (restated reference, all host cores)
+    python bench.py --impl reference [--max-cores C] ...   # the CPU arm
 
-A "step" is one pass of the hot path over one batch: counts_reduce (K1) over the synthetic
-mismatch matrix, then MAP + 6 NUTS runs + WAIC + posterior predictive + row assembly (K3-K7) for
-every TaxID that passes the cuts. Per-GPU workload (weak scaling): BASELINE config 2, "synthetic
-10k-TaxID mismatch matrix, +-15 positions" = 10 000 fitted TaxIDs per GPU (the generator keeps
-the ~47 000 TaxIDs that fail the cuts in the input so the cut/compaction path of K1 runs too).
+A "step" is one pass of the hot path over one batch: counts_reduce (K1) over the synthetic mismatch
+matrix, then MAP + 6 NUTS runs + WAIC + posterior predictive + row assembly (K3-K7) for every TaxID that
+passes the cuts. Steps are pipelined the way the CLI's per-file loop is (mdg_fit_batch_submit / _wait, two
+batches in flight per GPU): the tail of a batch — a handful of long sequential chains — runs under the bulk
+of the next one. All K steps are inside the timed region and the last one is drained before the clock stops.
 
-  value  whole-job fits/s with inputs resident in HBM (device pointers through the C-ABI)
-  e2e    the same through the host-buffer C-ABI calls the Python seams make (pinned host inputs,
-         H2D + D2H inside the timed region)
-  roofline         the dominant kernel (NUTS): SURVEY.md 8d flop model / CUDA-event time, against
-                   the FP64 FMA peak measured live on this GPU
-  roofline_counts  K1 on the 10M-row stress input (BASELINE config 5): 111 algorithmic B/row
-                   against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline     the oracle (C port of the reference algorithm; numpyro is not installable
-                   offline) on all host cores, on a bounded sample of the same workload
+Workload: N = 1 -> BASELINE config 2 (10 000 fitted TaxIDs, seed 20240001, +-15 positions).
+          N > 1 -> BASELINE config 3's generator (seed 20240002, min-alignments 10, min-y-sum 10), partitioned
+                   by TaxID over the GPUs: rank r fits its own contiguous share (`--taxa-per-gpu`, default
+                   40 000; the r-th jumped Philox block of the seed); at N = 8 one additional full-size pass
+                   (125 000 TaxIDs per GPU = 1M TaxIDs) is timed on its own and reported under `cfg3_full_pass`.
+
+  value            whole-job fits/s with inputs resident in HBM (device pointers through the C-ABI)
+  e2e              the same through the host-buffer C-ABI calls (pinned host inputs and outputs, H2D + D2H
+                   inside the timed region)
+  e2e_seam         N = 1: wall time of the reference-facing Python seams counts.compute_counts_with_dask(cfg) +
+                   fits.compute_fits(df_counts, cfg) on the same workload written as a TSV file
+  roofline         the dominant kernel (NUTS): SURVEY.md 8d flop model x gradient evaluations counted by the
+                   kernel / time during which a NUTS kernel was running (CUDA events on the launch streams),
+                   against the FP64 FMA peak measured live on this GPU (SM clock sampled during that kernel)
+  roofline_counts  K1 on the 10M-row stress input (BASELINE config 5): 111 algorithmic B/row against
+                   MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline     the reference on the host cores: numpyro itself if `import numpyro, jax` works (probed at run
+                   time), else the C restatement (oracle), on a bounded sample of the same workload
 """
 import argparse
 import json
@@ -40,6 +49,7 @@ UNIT = "fits/s"
 ALGO_BYTES_PER_ROW = 111
 # SURVEY.md 8d nominal FP64 flop model per log-density-gradient evaluation
 FLOPS_PER_GRAD = {0: 300 * 30 + 55, 1: 190 * 30 + 165, 2: 300 * 15 + 55, 3: 190 * 15 + 165, 4: 300 * 15 + 55, 5: 190 * 15 + 165}
+NCU_METRICS = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")  # written by tools/ncu_metrics.py from the .ncu-rep files
 
 
 def model_flops(leapfrogs, max_position):
@@ -47,13 +57,31 @@ def model_flops(leapfrogs, max_position):
     return sum(l * (FLOPS_PER_GRAD[r] * scale) for r, l in enumerate(leapfrogs))
 
 
-def workload(args, rank):
+def workload(args, rank, world, n_fit=None):
+    """Rank `rank`'s share of the workload (see the module docstring)."""
     from metadamage_b200 import synthetic as syn
 
-    seed = syn.SEEDS["cfg2"] + 1000 * rank
-    g = syn.make_mismatch_matrix(0, max_position=args.max_position, seed=seed, n_fit=args.taxa_per_gpu,
-                                 tax_id_start=1 + rank * 100_000_000)
-    return g
+    n_fit = n_fit or args.taxa_per_gpu
+    if world == 1:
+        return syn.make_mismatch_matrix(0, max_position=args.max_position, seed=syn.SEEDS["cfg2"], n_fit=n_fit)
+    return syn.make_mismatch_matrix(0, max_position=args.max_position, seed=syn.SEEDS["cfg3"], n_fit=n_fit, jump=rank,
+                                    tax_id_start=1 + rank * 100_000_000)
+
+
+def workload_config(args, world):
+    """The same dict for the GPU arm and the reference arm (the driver compares them)."""
+    P = args.max_position
+    if world == 1:
+        what = f"cfg2: synthetic heavy-tailed mismatch matrix, seed 20240001, {args.taxa_per_gpu} fitted TaxIDs"
+    else:
+        what = (f"cfg3 share: synthetic heavy-tailed mismatch matrix, seed 20240002, min-alignments 10, min-y-sum 10, partitioned by "
+                f"TaxID over {world} GPUs, {args.taxa_per_gpu} fitted TaxIDs per GPU and step")
+    return {
+        "workload": what + f", +-{P} positions, counts + MAP + 6 NUTS runs (500 warm-up + 1000 draws) + WAIC + predictive D_max",
+        "taxa_per_gpu": args.taxa_per_gpu, "max_position": P,
+        "partition": f"by TaxID over {world} GPU(s), no collective on the fit path",
+        "pipelining": "two batches in flight per GPU (mdg_fit_batch_submit / _wait); every step is drained inside the timed region",
+        "l2": "flushed between steps (256 MiB write); the counts inputs (>= 133 MB) exceed L2 as well"}
 
 
 class ClockSampler:
@@ -62,19 +90,21 @@ class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, period_ms=200):
         self.device = device
+        self.period_ms = period_ms
         self.lines = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -116,69 +146,94 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(g, args, n_sample=None, threads=0):
-    """The restated reference (oracle, C, OpenMP over TaxIDs) on a bounded sample."""
+def ncu_metric(kernel, key):
+    """A per-launch figure from the tool-generated summary of the committed ncu captures (None if absent)."""
+    try:
+        return json.load(open(NCU_METRICS))[kernel][key]
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the CPU arm
+# --------------------------------------------------------------------------------------------------------------
+def sample_size(n_fit, cores):
+    """ONE rule for every CPU leg: 64 TaxIDs per host thread (about 10 s of work), at most the whole workload."""
+    return max(8, min(int(n_fit), 64 * int(cores)))
+
+
+def cpu_baseline(g, cores, n_sample=None):
+    """The reference's algorithm on the host cores, on a bounded, evenly spread sample of the TaxIDs the GPU fits.
+    numpyro itself when it can be imported (kind "reference"), else the C restatement (kind "port")."""
+    sel = np.flatnonzero(g["passes"])
+    n_sample = n_sample or sample_size(len(sel), cores)
+    pick = sel[np.linspace(0, len(sel) - 1, n_sample).astype(int)]
+    from oracle import numpyro_arm
+
+    numpyro, why = numpyro_arm.probe()
+    if numpyro is not None and g["k"].shape[1] == 30:
+        try:
+            n_ref = max(200, min(n_sample, 256))
+            pick_ref = sel[np.linspace(0, len(sel) - 1, n_ref).astype(int)]
+            rows, t_first, t_rest = numpyro_arm.fit_rows(g["tax_ids"][pick_ref], g["k"][pick_ref], g["N"][pick_ref])
+            value = (n_ref - 1) / t_rest
+            return {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                    "sample": f"{n_ref} of the {len(sel)} fitted TaxIDs, evenly spread; the reference's own fit_single_group_without_timeout "
+                              f"(numpyro {numpyro.__version__}), one process; first fit incl. jit {t_first:.1f} s, the others {t_rest:.1f} s; "
+                              f"including the first fit: {n_ref / (t_first + t_rest):.3f} fits/s"}, t_first + t_rest
+        except Exception as exc:  # the probe found the modules but the reference does not run on them
+            why = f"numpyro importable but the reference did not run: {type(exc).__name__}: {exc}"
     from oracle import oracle as O
 
     O.build()
-    cores = threads or (os.cpu_count() or 1)
-    sel = np.flatnonzero(g["passes"])
-    n_sample = n_sample or max(8, min(len(sel), 64 * cores))  # ~10 s of CPU work on all cores
-    # an evenly spread sample of the same TaxIDs the GPU fits
-    pick = sel[np.linspace(0, len(sel) - 1, n_sample).astype(int)]
     cfg = O.default_config()
     t0 = time.perf_counter()
     out = O.fit_batch(g["tax_ids"][pick], g["k"][pick], g["N"][pick], cfg, n_threads=cores)
     dt = time.perf_counter() - t0
     ok = int(((out["result"]["status"] & 1) == 0).sum())
     return {"value": n_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_sample} of the {len(sel)} fitted TaxIDs of the same workload, evenly spread; "
+            "sample": f"{n_sample} of the {len(sel)} fitted TaxIDs of the same workload, evenly spread (64 per host thread); "
                       f"full fit (MAP + 6 NUTS runs 500+1000 + WAIC + predictive); {dt:.1f} s; {ok} ok; "
-                      "restated reference (numpyro unavailable offline)"}, dt
-
-
-def workload_config(args, world, n_in_tax=None, n_rows=None):
-    P = args.max_position
-    shape = f" ({n_in_tax} input TaxIDs, {n_rows} rows)" if n_in_tax else ""
-    return {
-        "workload": f"cfg2: synthetic heavy-tailed mismatch matrix, {args.taxa_per_gpu} fitted TaxIDs per GPU{shape}, "
-                    f"+-{P} positions, counts + MAP + 6 NUTS runs (500 warm-up + 1000 draws) + WAIC + predictive D_max",
-        "taxa_per_gpu": args.taxa_per_gpu, "max_position": P,
-        "partition": f"by TaxID over {world} GPU(s), no collective on the fit path",
-        "l2": "flushed between steps (256 MiB write)"}
+                      f"restated reference in C, OpenMP over TaxIDs (numpyro probe: {why})"}, dt
 
 
 def run_reference(args):
-    """The reference arm: the reference's algorithm on the host cores. numpyro/jax cannot be
-    installed offline, so this times the C restatement (oracle) with all host threads, each step
-    on a bounded, evenly spread sample of the same 10k-TaxID workload."""
+    """The reference arm: the reference's algorithm on the host cores, each step a bounded sample of the same
+    workload and configuration as the GPU arm. Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    g = workload(args, 0)
-    cores = os.cpu_count() or 1
+    world = max(1, args.gpus)
+    if world > 1 and args.taxa_per_gpu is None:
+        args.taxa_per_gpu = 40_000
+    args.taxa_per_gpu = args.taxa_per_gpu or 10_000
+    cores = args.max_cores or os.cpu_count() or 1
+    # the sample is drawn from rank 0's share of the GPU arm's workload; a bounded share is enough to draw it from
+    g = workload(args, 0, world, n_fit=min(args.taxa_per_gpu, 10_000))
     n_fit = int(g["passes"].sum())
-    n_sample = max(8, min(n_fit, 32 * cores))
-    for _ in range(args.warmup):
-        cpu_baseline(g, args, n_sample=max(4, 2 * cores))
+    n_sample = sample_size(n_fit, cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(g, cores, n_sample=max(4, 2 * cores))
     times, last = [], None
     for _ in range(args.steps):
-        last, dt = cpu_baseline(g, args, n_sample=n_sample)
+        last, dt = cpu_baseline(g, cores, n_sample=n_sample)
         times.append(dt)
-    value = n_sample * len(times) / sum(times)
+    n_eff = n_sample if last["kind"] == "port" else None
+    value = (n_sample * len(times) / sum(times)) if n_eff else last["value"]
     last["value"] = value
-    cfg = workload_config(args, args.gpus, len(g["tax_ids"]), len(g["tax_id"]))
-    cfg["reference_sample_per_step"] = n_sample
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------------------
+# the GPU arm
+# --------------------------------------------------------------------------------------------------------------
 def counts_stress(ctx, torch, dev, n_rows=10_000_000, reps=5):
     """BASELINE config 5: 10M-row counts aggregation, device resident, HBM-bound."""
     P = 15
@@ -212,14 +267,39 @@ def counts_stress(ctx, torch, dev, n_rows=10_000_000, reps=5):
     ms = float(np.mean(times[2:]))
     peak, which = hbm_peak()
     achieved = ALGO_BYTES_PER_ROW * n_rows / (ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this 10M-row input, from the ncu --set full
-    # capture summarised in profiles/r01_counts_ncu.md (460 MB + 255 MB); not re-measured live
-    traffic = 715e6 if n_rows == 10_000_000 else None
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_source": "ncu --set full capture (profiles/r01_counts_ncu.md), bytes per launch",
-            "kernel": "counts_reduce_kernel", "rows": n_rows, "kept_taxa": int(kept), "kernel_ms": ms,
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_metric("counts", "dram_bytes_per_launch") if n_rows == 10_000_000 else None,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, read by tools/ncu_metrics.py from the committed "
+                              "ncu --set full capture (profiles/r02_ncu_metrics.json); null if that file is absent",
+            "kernel": "counts kernels (K1) of one mdg_counts_reduce call", "rows": n_rows, "kept_taxa": int(kept), "kernel_ms": ms,
             "algorithmic_bytes_per_row": ALGO_BYTES_PER_ROW, "peak_source": which,
-            "note": "inputs (780 MB) exceed L2; mean of %d launches after 2 warm-ups, CUDA events on the launch stream" % reps}
+            "note": "inputs (780 MB) exceed L2; mean of %d calls after 2 warm-ups, CUDA events on the launch stream" % reps}
+
+
+class DeviceBatch:
+    """Device-resident inputs of one workload plus two sets of output buffers (two steps are in flight)."""
+
+    def __init__(self, torch, dev, g, R):
+        from metadamage_b200._abi import FIT_RESULT_DTYPE
+
+        n_rows, n_in_tax = len(g["tax_id"]), len(g["tax_ids"])
+        self.n_rows, self.n_in_tax = n_rows, n_in_tax
+        self.cols = dict(
+            tax_id=torch.from_numpy(g["tax_id"]).to(dev), n_alignments=torch.from_numpy(g["n_alignments"].view(np.int32)).to(dev),
+            is_reverse=torch.from_numpy(g["is_reverse"]).to(dev), pos0=torch.from_numpy(g["pos0"]).to(dev),
+            counts16=torch.from_numpy(g["counts16"].view(np.int32)).to(dev))
+        self.sets = []
+        for _ in range(2):
+            outs = dict(
+                n_fwd_ref=torch.empty(n_rows, dtype=torch.int32, device=dev), n_rev_ref=torch.empty(n_rows, dtype=torch.int32, device=dev),
+                f_fwd=torch.empty(n_rows, dtype=torch.float32, device=dev), f_rev=torch.empty(n_rows, dtype=torch.float32, device=dev),
+                z=torch.empty(n_rows, dtype=torch.int8, device=dev), y_sum_total=torch.empty(n_rows, dtype=torch.int64, device=dev),
+                keep=torch.empty(n_rows, dtype=torch.uint8, device=dev), tax_id=torch.empty(n_in_tax, dtype=torch.int64, device=dev),
+                n_alignments=torch.empty(n_in_tax, dtype=torch.int32, device=dev), first_row=torch.empty(n_in_tax, dtype=torch.int64, device=dev),
+                k=torch.empty((n_in_tax, R), dtype=torch.int32, device=dev), N=torch.empty((n_in_tax, R), dtype=torch.int32, device=dev),
+                noise=torch.empty((n_in_tax, 3), dtype=torch.float64, device=dev))
+            self.sets.append(dict(outs=outs, res=torch.empty(n_in_tax * FIT_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev),
+                                  med=torch.empty((3, n_in_tax, R), dtype=torch.float32, device=dev)))
 
 
 def main():
@@ -228,10 +308,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--taxa-per-gpu", type=int, default=10_000, help="fitted TaxIDs per GPU per step (cfg2: 10k; cfg3: 125k at 8 GPUs)")
+    ap.add_argument("--taxa-per-gpu", type=int, default=None,
+                    help="fitted TaxIDs per GPU per step (default: 10 000 = cfg2 on 1 GPU, 40 000 of cfg3's generator on N > 1)")
     ap.add_argument("--max-position", type=int, default=15)
+    ap.add_argument("--max-cores", type=int, default=0, help="host threads of the CPU arm (default: all; the reference CLI's --max-cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-counts-stress", action="store_true")
+    ap.add_argument("--no-seam", action="store_true")
+    ap.add_argument("--no-full-pass", action="store_true", help="skip the 1M-TaxID single pass at N = 8")
+    ap.add_argument("--heuristic", type=int, default=0, help="find_heuristic_step_size (0 = numpyro 0.4.1 default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -248,6 +333,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.taxa_per_gpu is None:
+        args.taxa_per_gpu = 10_000 if world == 1 else 40_000
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -256,74 +343,83 @@ def main():
     ctx = Context(local_rank)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
-    cfg = _lib.default_config()
+    cfg = _lib.default_config(find_heuristic_step_size=args.heuristic)
     P = args.max_position
     R = 2 * P
 
-    g = workload(args, rank)
-    n_rows = len(g["tax_id"])
-    n_in_tax = len(g["tax_ids"])
-
-    # ---------------- device-resident buffers (value) ----------------
-    cols = dict(
-        tax_id=torch.from_numpy(g["tax_id"]).to(dev), n_alignments=torch.from_numpy(g["n_alignments"].view(np.int32)).to(dev),
-        is_reverse=torch.from_numpy(g["is_reverse"]).to(dev), pos0=torch.from_numpy(g["pos0"]).to(dev),
-        counts16=torch.from_numpy(g["counts16"].view(np.int32)).to(dev))
-    outs = dict(
-        n_fwd_ref=torch.empty(n_rows, dtype=torch.int32, device=dev), n_rev_ref=torch.empty(n_rows, dtype=torch.int32, device=dev),
-        f_fwd=torch.empty(n_rows, dtype=torch.float32, device=dev), f_rev=torch.empty(n_rows, dtype=torch.float32, device=dev),
-        z=torch.empty(n_rows, dtype=torch.int8, device=dev), y_sum_total=torch.empty(n_rows, dtype=torch.int64, device=dev),
-        keep=torch.empty(n_rows, dtype=torch.uint8, device=dev), tax_id=torch.empty(n_in_tax, dtype=torch.int64, device=dev),
-        n_alignments=torch.empty(n_in_tax, dtype=torch.int32, device=dev), first_row=torch.empty(n_in_tax, dtype=torch.int64, device=dev),
-        k=torch.empty((n_in_tax, R), dtype=torch.int32, device=dev), N=torch.empty((n_in_tax, R), dtype=torch.int32, device=dev),
-        noise=torch.empty((n_in_tax, 3), dtype=torch.float64, device=dev))
-    res_dev = torch.empty(n_in_tax * FIT_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    med_dev = torch.empty((3, n_in_tax, R), dtype=torch.float32, device=dev)
+    g = workload(args, rank, world)
+    batch = DeviceBatch(torch, dev, g, R)
+    n_rows, n_in_tax = batch.n_rows, batch.n_in_tax
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    stats = {"counts_ms": [], "map_ms": [], "nuts_ms": [], "ppc_ms": [], "assemble_ms": [], "launches": 0, "leapfrogs": np.zeros(6)}
+    stats = {"counts_ms": [], "map_ms": [], "nuts_ms": [], "nuts_union_ms": [], "ppc_ms": [], "assemble_ms": [], "launches": 0,
+             "leapfrogs": np.zeros(6)}
 
-    def step_device(record):
-        flush.zero_()  # evict L2 between steps
-        n_fit = ctx.counts_reduce_device(cols, outs)
-        t1 = ctx.timings()
-        ctx.fit_batch_device(outs["tax_id"][:n_fit], outs["k"][:n_fit], outs["N"][:n_fit], res_dev, cfg,
-                             median=med_dev[0], hpdi_lo=med_dev[1], hpdi_hi=med_dev[2], noise3=outs["noise"][:n_fit])
-        t2 = ctx.timings()
-        if record:
-            stats["counts_ms"].append(t1["counts_ms"])
-            for key in ("map_ms", "nuts_ms", "ppc_ms", "assemble_ms"):
-                stats[key].append(t2[key])
-            stats["launches"] += t1["n_launches"] + t2["n_launches"]
-            stats["leapfrogs"] += np.array(t2["leapfrogs"], dtype=np.float64)
-        return n_fit
+    def book(t_counts, t_fit, record):
+        if not record:
+            return
+        if t_counts is not None:
+            stats["counts_ms"].append(t_counts["counts_ms"])
+            stats["launches"] += t_counts["n_launches"]
+        if t_fit is not None:
+            for key in ("map_ms", "nuts_ms", "nuts_union_ms", "ppc_ms", "assemble_ms"):
+                stats[key].append(t_fit[key])
+            stats["launches"] += t_fit["n_launches"]
+            stats["leapfrogs"] += np.array(t_fit["leapfrogs"], dtype=np.float64)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(step_fn, steps):
+    def run_pipelined(steps, submit, record=True):
+        """`submit(i)` enqueues step i and returns (n_fit, ticket, counts timings); at most two steps in flight."""
+        pending, n = None, 0
+        for i in range(steps):
+            n_fit, ticket, t_counts = submit(i)
+            book(t_counts, None, record)
+            n += n_fit
+            if pending is not None:
+                book(None, ctx.fit_wait(pending)["timings"], record)
+            pending = ticket
+        if pending is not None:
+            last = ctx.fit_wait(pending)
+            book(None, last["timings"], record)
+            return n, last
+        return n, None
+
+    def timed(steps, submit, record=True):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        n = 0
-        for _ in range(steps):
-            n += step_fn(True)
-        e1.record(stream)
+        n, last = run_pipelined(steps, submit, record)
+        e1.record(stream)  # fit_wait ordered the ctx stream after every batch
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         cnt = torch.tensor([float(n)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        return float(ms.item()), float(cnt.item())
+        return float(ms.item()), float(cnt.item()), last
 
-    for _ in range(args.warmup):
-        step_device(False)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    dev_ms, dev_fits = timed(step_device, args.steps)
+    def make_submit_device(b, fit_cfg):
+        def submit(i):
+            s = b.sets[i % 2]
+            flush.zero_()  # evict L2 between steps
+            n_fit = ctx.counts_reduce_device(b.cols, s["outs"])
+            t1 = ctx.timings()
+            o = s["outs"]
+            ticket = ctx.fit_submit_device(o["tax_id"][:n_fit], o["k"][:n_fit], o["N"][:n_fit], s["res"], fit_cfg,
+                                           median=s["med"][0], hpdi_lo=s["med"][1], hpdi_hi=s["med"][2], noise3=o["noise"][:n_fit])
+            return n_fit, ticket, t1
+        return submit
+
+    # ---------------- device-resident path (value) ----------------
+    submit_device = make_submit_device(batch, cfg)
+    if args.warmup:
+        run_pipelined(args.warmup, submit_device, record=False)
+    sampler = ClockSampler(local_rank).start()
+    dev_ms, dev_fits, _ = timed(args.steps, submit_device)
 
     # ---------------- host-buffer path (e2e) ----------------
     def pinned(a):
@@ -332,105 +428,128 @@ def main():
         t.numpy()[...] = view
         return t.numpy().view(a.dtype)
 
-    h = {key: pinned(g[key]) for key in ("tax_id", "n_alignments", "is_reverse", "pos0", "counts16")}
-    e2e_bytes = {"h2d": 0, "d2h": 0}
-
     def pinned_empty(shape, dtype):
+        shape = shape if isinstance(shape, tuple) else (shape,)
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
         return t.numpy()[:nbytes].view(dtype).reshape(shape)
 
-    # result buffers of the host API, pinned and reused from step to step (Context.counts_reduce(out=...))
-    host_out = dict(
-        n_fwd_ref=pinned_empty(n_rows, np.uint32), n_rev_ref=pinned_empty(n_rows, np.uint32), f_fwd=pinned_empty(n_rows, np.float32),
-        f_rev=pinned_empty(n_rows, np.float32), z=pinned_empty(n_rows, np.int8), y_sum_total=pinned_empty(n_rows, np.uint64),
-        keep=pinned_empty(n_rows, np.uint8), tax_id=pinned_empty(n_in_tax, np.int64), n_alignments=pinned_empty(n_in_tax, np.uint32),
-        first_row=pinned_empty(n_in_tax, np.int64), k=pinned_empty((n_in_tax, R), np.uint32), N=pinned_empty((n_in_tax, R), np.uint32),
-        noise=pinned_empty((n_in_tax, 3), np.float64))
+    h = {key: pinned(g[key]) for key in ("tax_id", "n_alignments", "is_reverse", "pos0", "counts16")}
+    e2e_bytes = {"h2d": 0, "d2h": 0}
+    host_sets = []
+    for _ in range(2):
+        host_sets.append(dict(
+            counts=dict(
+                n_fwd_ref=pinned_empty(n_rows, np.uint32), n_rev_ref=pinned_empty(n_rows, np.uint32), f_fwd=pinned_empty(n_rows, np.float32),
+                f_rev=pinned_empty(n_rows, np.float32), z=pinned_empty(n_rows, np.int8), y_sum_total=pinned_empty(n_rows, np.uint64),
+                keep=pinned_empty(n_rows, np.uint8), tax_id=pinned_empty(n_in_tax, np.int64), n_alignments=pinned_empty(n_in_tax, np.uint32),
+                first_row=pinned_empty(n_in_tax, np.int64), k=pinned_empty((n_in_tax, R), np.uint32), N=pinned_empty((n_in_tax, R), np.uint32),
+                noise=pinned_empty((n_in_tax, 3), np.float64)),
+            fit=dict(result=pinned_empty(n_in_tax, FIT_RESULT_DTYPE), median=pinned_empty((n_in_tax, R), np.float32),
+                     hpdi_lo=pinned_empty((n_in_tax, R), np.float32), hpdi_hi=pinned_empty((n_in_tax, R), np.float32))))
 
-    def step_host(record):
+    def submit_host(i):
+        s = host_sets[i % 2]
         flush.zero_()
         r = ctx.counts_reduce(h["tax_id"], h["n_alignments"], h["is_reverse"], h["pos0"], h["counts16"],
-                              max_position=P, want_noise=True, out=host_out)
+                              max_position=P, want_noise=True, out=s["counts"])
         t1 = ctx.timings()
-        out = ctx.fit_batch(r["tax_id"], r["k"], r["N"], cfg, noise3=r["noise"])
-        t2 = ctx.timings()
-        if record:
-            stats["launches"] += t1["n_launches"] + t2["n_launches"]
-            stats["chain_leapfrogs"] = out["result"]["run"]["n_leapfrog"]
-            n_fit = r["n_tax"]
-            e2e_bytes["h2d"] = sum(h[key].nbytes for key in h) + n_fit * (8 + 2 * R * 4 + 24)
-            e2e_bytes["d2h"] = (n_rows * (4 + 4 + 4 + 4 + 1 + 8 + 1) + n_fit * (8 + 4 + 8 + 2 * R * 4 + 24)
-                                + out["result"].nbytes + 3 * out["median"].nbytes)
-        return r["n_tax"]
+        ticket = ctx.fit_submit(r["tax_id"], r["k"], r["N"], cfg, noise3=r["noise"], out=s["fit"])
+        n_fit = r["n_tax"]
+        e2e_bytes["h2d"] = sum(h[key].nbytes for key in h) + n_fit * (8 + 2 * R * 4 + 24)
+        e2e_bytes["d2h"] = (n_rows * (4 + 4 + 4 + 4 + 1 + 8 + 1) + n_fit * (8 + 4 + 8 + 2 * R * 4 + 24)
+                            + n_fit * (FIT_RESULT_DTYPE.itemsize + 3 * R * 4))
+        return n_fit, ticket, t1
 
-    step_host(False)
-    e2e_ms, e2e_fits = timed(step_host, args.steps)
+    run_pipelined(1, submit_host, record=False)
+    e2e_ms, e2e_fits, last_host = timed(args.steps, submit_host)
     clocks = sampler.stop()
+    chain_leapfrogs = np.array(last_host["result"]["run"]["n_leapfrog"], dtype=np.float64)
+    status = np.array(last_host["result"]["status"])
 
     # ---------------- the north star's reduced unit: no forward-only / reverse-only refits ----------------
-    cfg_reduced = cfg.copy(do_fwd_rev=0)
+    submit_reduced = make_submit_device(batch, cfg.copy(do_fwd_rev=0))
+    run_pipelined(1, submit_reduced, record=False)
+    red_ms, red_fits, _ = timed(1, submit_reduced, record=False)
 
-    def step_reduced(record):
-        flush.zero_()
-        n_fit = ctx.counts_reduce_device(cols, outs)
-        ctx.fit_batch_device(outs["tax_id"][:n_fit], outs["k"][:n_fit], outs["N"][:n_fit], res_dev, cfg_reduced,
-                             median=med_dev[0], hpdi_lo=med_dev[1], hpdi_hi=med_dev[2], noise3=outs["noise"][:n_fit])
-        if record:
-            stats["launches"] += 3 + ctx.timings()["n_launches"]
-        return n_fit
+    # ---------------- N = 8: one full-size pass of BASELINE config 3 (1M TaxIDs over the box) ----------------
+    full_pass = None
+    if world == 8 and not args.no_full_pass:
+        del batch, submit_device, submit_reduced
+        torch.cuda.empty_cache()
+        n_full = 1_000_000 // world
+        gf = workload(args, rank, world, n_fit=n_full)
+        bf = DeviceBatch(torch, dev, gf, R)
+        submit_full = make_submit_device(bf, cfg)
+        run_pipelined(1, submit_full, record=False)
+        fs = ClockSampler(local_rank).start()
+        t_wall = time.perf_counter()
+        full_ms, full_fits, _ = timed(1, submit_full, record=False)
+        t_wall = time.perf_counter() - t_wall
+        full_pass = {"taxids": int(full_fits), "ms": full_ms, "value": full_fits / (full_ms * 1e-3), "unit": UNIT, "steps": 1,
+                     "wall_s_incl_barriers": t_wall, "clocks": fs.stop(),
+                     "what": "ONE pass over 1M fitted TaxIDs (125 000 per GPU, cfg3 generator, seed 20240002, rank r = jumped block r), "
+                             "device resident, after one untimed pass; max over ranks of the CUDA-event time"}
 
-    step_reduced(False)
-    red_ms, red_fits = timed(step_reduced, 1)
-
-    # ---------------- longest chain (the tail of a step is one sequential Markov chain) ----------------
-    chains = stats["chain_leapfrogs"].astype(np.float64)
-    chain_max = torch.tensor([chains.max()], dtype=torch.float64, device=dev)
-    chain_sum = torch.tensor([chains.sum(), float(chains.size)], dtype=torch.float64, device=dev)
+    # ---------------- longest chain (a step's tail is a few sequential Markov chains) ----------------
+    chain_max = torch.tensor([chain_leapfrogs.max()], dtype=torch.float64, device=dev)
+    chain_sum = torch.tensor([chain_leapfrogs.sum(), float(chain_leapfrogs.size)], dtype=torch.float64, device=dev)
+    # per-rank roofline inputs: NUTS-active seconds and model flops of this rank's timed device + host steps
+    nuts_s = float(np.sum(stats["nuts_union_ms"])) * 1e-3
+    flops = model_flops(list(stats["leapfrogs"]), P)
+    rank_tf = torch.tensor([flops / nuts_s / 1e12 if nuts_s > 0 else 0.0], dtype=torch.float64, device=dev)
+    all_tf = [rank_tf.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(chain_max, op=dist.ReduceOp.MAX)
         dist.all_reduce(chain_sum, op=dist.ReduceOp.SUM)
+        dist.all_gather(all_tf, rank_tf)
+    per_rank_tf = [float(t.item()) for t in all_tf]
     chain_stats = {"mean_leapfrogs_per_chain": float(chain_sum[0].item() / chain_sum[1].item()),
                    "max_leapfrogs_of_one_chain": float(chain_max.item()),
-                   "note": "a step cannot end before its longest chain does: a chain is sequential (one warp; measured 1.9 us per leapfrog "
-                           "with the GPU to itself, ~3.4 us averaged over a full batch); rarely (one chain in the 480 000 of the eight bench "
-                           "shards: 464 068 leapfrogs, in rank 1's) a chain adapts to a collapsed step size and runs ~50x the mean "
-                           "(DESIGN.md section 7, profiles/r01_shard_probe.log)"}
+                   "failed_fits_rank0": int((status & 1).sum()),
+                   "note": "a chain is sequential; the tail of a batch (its longest chains) runs under the next batch"}
 
-    # ---------------- rooflines, CPU baseline (rank 0 only) ----------------
+    # ---------------- rooflines, seam, CPU baseline (rank 0 only) ----------------
     if rank == 0:
-        fp64_peak = ctx.fp64_peak_tflops()
-        nuts_ms = float(np.sum(stats["nuts_ms"]))
-        flops = model_flops(list(stats["leapfrogs"]), P)
-        achieved = flops / (nuts_ms * 1e-3) / 1e12 if nuts_ms > 0 else 0.0
+        peak_sampler = ClockSampler(local_rank, period_ms=50).start()
+        fp64_peak = max(ctx.fp64_peak_tflops() for _ in range(12))  # ~1 s of DFMA so that the clock sampler sees it
+        peak_clocks = peak_sampler.stop()
+        evals = float(stats["leapfrogs"].sum())
+        achieved = per_rank_tf[0]
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            "traffic": 948.0, "traffic_source": "ncu --set full capture of the PMD/all launch (profiles/r01_nuts_ncu.md): bytes of DRAM traffic per launch, i.e. none",
-            "kernel": "nuts_kernel<PMD|null, 32|16 lanes> (4 launches per step)",
+            "traffic": ncu_metric("nuts", "dram_bytes_per_launch"),
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one NUTS launch, read by tools/ncu_metrics.py from the committed "
+                              "ncu --set full capture (profiles/r02_ncu_metrics.json); null if that file is absent",
+            "kernel": "nuts_group_kernel<PMD|null, 8 lanes per chain> (4 launches per batch)",
             "flop_model": "SURVEY.md 8d nominal: PMD 300*n_obs+55, null 190*n_obs+165 flop per gradient evaluation",
-            "gradient_evaluations_per_step": float(stats["leapfrogs"].sum() / max(1, args.steps)),
-            "gradient_evaluations_per_s": float(stats["leapfrogs"].sum() / (nuts_ms * 1e-3)) if nuts_ms > 0 else 0.0,
-            "peak_source": "FP64 FMA peak measured live on this GPU (mdg_measure_fp64_peak); not in MEASURED_PEAKS.json",
-            "ncu": {"source": "profiles/r01_nuts_ncu.md (ncu --set full, PMD/all launch; static, not re-measured by this run)",
-                    "warp_instructions_per_evaluation": 1096, "fp64_instruction_share": 0.414,
-                    "executed_fp64_flop_per_evaluation": 20850,
-                    "executed_fp64_tflops_at_this_rate": 20850 * float(stats["leapfrogs"].sum() / (nuts_ms * 1e-3)) / 1e12 if nuts_ms > 0 else 0.0,
-                    "fp64_pipe_busy_full_size": 0.48, "ipc_per_scheduler_full_size": 0.58,
-                    "pipe_busy_pct_in_capture": {"fp64": 33.3, "alu": 14.8, "xu_sfu": 7.4, "fma_fp32": 5.5, "lsu": 25.5, "issue_slots": 46.5}},
+            "gradient_evaluations": evals,
+            "nuts_active_s": nuts_s,
+            "gradient_evaluations_per_s": evals / nuts_s if nuts_s > 0 else 0.0,
+            "time_base": "union over the pipelined batches of the CUDA-event intervals [first NUTS launch, last NUTS launch done] "
+                         "(mdg_timings.nuts_union_ms), device and host steps of the timed regions",
+            "peak_source": "FP64 FMA peak measured live on this GPU (mdg_measure_fp64_peak, best of 12 x 3 launches); not in MEASURED_PEAKS.json",
+            "peak_clocks": peak_clocks,
+            "over_ranks": {"min": min(per_rank_tf), "mean": float(np.mean(per_rank_tf)), "max": max(per_rank_tf), "unit": "TFLOP/s"},
             "note": "HBM traffic of the fit kernels is negligible (240 B in, ~1 KB out per TaxID): compute bound, no tensor cores",
         }
         roofline_counts = None if args.no_counts_stress else counts_stress(ctx, torch, dev)
+        seam = None
+        if world == 1 and not args.no_seam:
+            seam = seam_timing(g, args, e2e_ms / args.steps)
         cpu = None
         if not args.no_cpu_baseline:
-            cpu, _ = cpu_baseline(g, args)
+            cpu, _ = cpu_baseline(g, args.max_cores or os.cpu_count() or 1)
         per_step = lambda key: float(np.mean(stats[key])) if stats[key] else 0.0  # noqa: E731
         line = {
             "metric": METRIC, "value": dev_fits / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world, n_in_tax, n_rows),
+            "config": workload_config(args, world),
+            "input_shape_rank0": {"input_taxids": n_in_tax, "rows": n_rows},
             "e2e": {"value": e2e_fits / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(e2e_bytes["h2d"]),
                     "d2h_bytes_per_step": int(e2e_bytes["d2h"]), "ms_per_step": e2e_ms / args.steps},
+            "e2e_seam": seam,
             "gpu_launches": int(stats["launches"]),
             "clocks": clocks,
             "roofline": roofline,
@@ -438,16 +557,51 @@ def main():
             "chains": chain_stats,
             "reduced_unit": {"value": red_fits / (red_ms * 1e-3), "unit": UNIT, "ms_per_step": red_ms, "steps": 1,
                              "what": "counts + MAP + PMD/null NUTS on all positions + WAIC + predictive D_max, WITHOUT the forward-only / "
-                                     "reverse-only refits of fits.py:298-356 (the north star's reduced unit; `value` above is the full fit)"},
+                                     "reverse-only refits of fits.py:298-356 (the north star's reduced unit; `value` above is the full fit); "
+                                     "one unpipelined step"},
+            "cfg3_full_pass": full_pass,
             "cpu_baseline": cpu,
             "kernel_ms_per_step": {"counts": per_step("counts_ms"), "map": per_step("map_ms"), "nuts": per_step("nuts_ms"),
-                                   "ppc": per_step("ppc_ms"), "assemble": per_step("assemble_ms")},
+                                   "nuts_union": per_step("nuts_union_ms"), "ppc": per_step("ppc_ms"), "assemble": per_step("assemble_ms")},
+            "find_heuristic_step_size": args.heuristic,
         }
         print(json.dumps(line), flush=True)
     barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def seam_timing(g, args, abi_e2e_ms):
+    """Wall time of the reference-facing seams on the same workload as a file: counts.compute_counts_with_dask(cfg)
+    (file -> df_counts: GPU tokeniser + K1 + DataFrame) and fits.compute_fits(df_counts, cfg, mcmc_kwargs)
+    (df_counts -> two DataFrames), the calls main.py:57,66 make. The second of two runs is reported."""
+    import tempfile
+
+    from metadamage_b200 import counts, fits, synthetic as syn, utils
+
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "cfg2.mismatch.txt")
+        syn.write_tsv(g, path)
+        cfg = utils.Config(out_dir=os.path.join(tmp, "out"), max_fits=None, max_cores=1, max_position=args.max_position, min_alignments=10,
+                           min_y_sum=10, substitution_bases_forward="CT", substitution_bases_reverse="GA", forced=True, version="bench")
+        cfg.add_filename(path)
+        out = {}
+        for rep in range(2):
+            t0 = time.perf_counter()
+            df_counts = counts.compute_counts_with_dask(cfg)
+            t1 = time.perf_counter()
+            df_res, df_pred = fits.compute_fits(df_counts, cfg, fits.mcmc_kwargs_default())
+            t2 = time.perf_counter()
+            out = {"counts_s": t1 - t0, "fits_s": t2 - t1, "total_s": t2 - t0, "fitted_taxids": int(len(df_res)),
+                   "df_counts_rows": int(len(df_counts)), "file_bytes": os.path.getsize(path)}
+    out["value"] = out["fitted_taxids"] / out["total_s"]
+    out["unit"] = UNIT
+    out["overhead_vs_abi_e2e"] = out["total_s"] / (abi_e2e_ms * 1e-3) - 1.0
+    out["what"] = ("wall clock of counts.compute_counts_with_dask(cfg) + fits.compute_fits(df_counts, cfg, mcmc_kwargs) on the cfg2 workload "
+                   "written as a 22-column TSV (file read, GPU tokeniser, K1, DataFrames, K3-K7, result DataFrames included; one "
+                   "unpipelined batch), second of two runs; overhead is relative to one pipelined C-ABI e2e step")
+    return out
 
 
 def _json_only_stdout():

@@ -235,6 +235,20 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows,
                       int64_t out_capacity, int64_t* out_n_tax /* host pointer */);
 
 /*
+ * K1d — counts_order: the row order of df_counts (counts.py:167-172 sort_by_alignments; C8 of SURVEY.md 8a).
+ * The reference sorts ROWS by (N_alignments desc, tax_id desc, 1/z for z > 0 else z desc). Rows of a TaxID
+ * are contiguous and share N_alignments and tax_id, so the caller sorts the n_tax per-TaxID keys
+ * (`tax_order[i]` = index into the per-TaxID arrays of mdg_counts_reduce of the TaxID that comes i-th) and this
+ * call produces the row-level permutation: out_perm[j] = input row of output row j, over the kept rows only
+ * (keep_row NULL = all rows), z = +1..+P then -1..-P inside a TaxID, ties in input order (stable).
+ * *out_n_rows (host pointer) = number of kept rows written (<= perm_capacity, else MDG_ERR_INVALID).
+ */
+int mdg_counts_order(mdg_ctx* ctx, int mem, int64_t n_rows,
+                     const int64_t* tax_id_row, const int8_t* z_row, const uint8_t* keep_row,
+                     int64_t n_tax, const int64_t* first_row, const int64_t* tax_order,
+                     int64_t* out_perm, int64_t perm_capacity, int64_t* out_n_rows /* host pointer */);
+
+/*
  * K3-K7 — fit a dense batch of TaxIDs. Replaces fits.py:428-469 for every TaxID.
  * k, N: [n_tax][2*max_position] (layout above). mism12: optional [n_tax][2*max_position][12]
  * raw off-diagonal counts in column order AC,AG,AT,CA,CG,CT,GA,GC,GT,TA,TC,TG for the noise

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "mdg_ctx_get_timings",
     "mdg_fit_config_default",
     "mdg_counts_reduce",
+    "mdg_counts_order",
     "mdg_tsv_parse",
     "mdg_fit_batch",
     "mdg_fit_batch_submit",
@@ -70,6 +71,7 @@ def load():
     lib.mdg_counts_reduce.argtypes = (
         [vp, i32, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, u32, u64] + [vp] * 13 + [i64, C.POINTER(i64)]
     )
+    lib.mdg_counts_order.argtypes = [vp, i32, i64, vp, vp, vp, i64, vp, vp, vp, i64, C.POINTER(i64)]
     lib.mdg_tsv_parse.argtypes = [vp, i32, C.c_char_p, i64, i64, vp, vp, vp, vp, vp, i64, vp, vp, C.POINTER(i64), C.POINTER(C.c_int32)]
     lib.mdg_fit_batch.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, C.POINTER(FitConfig)] + [vp] * 7
     lib.mdg_fit_batch_submit.argtypes = lib.mdg_fit_batch.argtypes + [C.POINTER(i64)]

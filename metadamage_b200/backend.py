@@ -18,11 +18,12 @@ def _base_index(sub):
     return BASES.index(sub[0]), BASES.index(sub[1])
 
 
-def _dptr(t):
-    """device pointer of a contiguous torch CUDA tensor (None -> NULL)"""
+def _dptr(t, rows_ok=False):
+    """device pointer of a contiguous torch CUDA tensor (None -> NULL); `rows_ok`: a 2-D tensor whose rows are
+    contiguous (a column range of a wider buffer; the row stride is passed separately) is accepted too"""
     if t is None:
         return None
-    if not t.is_cuda or not t.is_contiguous():
+    if not t.is_cuda or not (t.is_contiguous() or (rows_ok and t.dim() == 2 and t.stride(1) == 1)):
         raise ValueError("device buffers must be contiguous CUDA tensors")
     return C.c_void_p(t.data_ptr())
 
@@ -100,6 +101,31 @@ class Context:
         res["n_rows"], res["n_cols"] = n, n_cols.value
         return res
 
+    def tsv_parse_device(self, text, want_spans=False):
+        """K0 with the parsed columns left on the GPU (torch CUDA tensors), ready for `counts_reduce_device`:
+        nothing but the text crosses PCIe. Returns (cols, n_rows, n_cols); `cols` also carries `name_span` /
+        `rank_span` ([rows][2] int64, 22-column layout) when asked for."""
+        import torch
+
+        if not isinstance(text, (bytes, bytearray, memoryview)):
+            raise TypeError("text must be bytes")
+        text = bytes(text)
+        cap = text.count(b"\n") + 1
+        dev = torch.device("cuda", self.device)
+        cols = dict(tax_id=torch.empty(cap, dtype=torch.int64, device=dev), n_alignments=torch.empty(cap, dtype=torch.int32, device=dev),
+                    is_reverse=torch.empty(cap, dtype=torch.uint8, device=dev), pos0=torch.empty(cap, dtype=torch.uint8, device=dev),
+                    counts16=torch.empty((16, cap), dtype=torch.int32, device=dev))
+        if want_spans:
+            cols["name_span"] = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+            cols["rank_span"] = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+        n_rows, n_cols = C.c_int64(0), C.c_int32(0)
+        _lib.check(self._lib.mdg_tsv_parse(self._h, MDG_DEVICE, text, len(text), cap, _dptr(cols["tax_id"]), _dptr(cols["n_alignments"]),
+                                           _dptr(cols["is_reverse"]), _dptr(cols["pos0"]), _dptr(cols["counts16"]), cap,
+                                           _dptr(cols.get("name_span")), _dptr(cols.get("rank_span")), C.byref(n_rows), C.byref(n_cols)))
+        n = n_rows.value
+        out = {key: (val[:n] if key != "counts16" else val[:, :n]) for key, val in cols.items()}
+        return out, n, n_cols.value
+
     # ------------------------------------------------------------------ K1
     def counts_reduce(self, tax_id, n_alignments, is_reverse, pos0, counts16, fwd="CT", rev="GA",
                       max_position=15, min_alignments=10, min_y_sum=10, want_noise=False, want_rows=True, out=None):
@@ -173,11 +199,35 @@ class Context:
         g = lambda k: _dptr(outs.get(k))  # noqa: E731
         _lib.check(self._lib.mdg_counts_reduce(
             self._h, MDG_DEVICE, n, _dptr(cols["tax_id"]), _dptr(cols["n_alignments"]), _dptr(cols["is_reverse"]),
-            _dptr(cols["pos0"]), _dptr(cols["counts16"]), cols["counts16"].stride(0),
+            _dptr(cols["pos0"]), _dptr(cols["counts16"], rows_ok=True), cols["counts16"].stride(0),
             fr, fo, rr, ro, int(max_position), int(min_alignments), int(min_y_sum),
             g("n_fwd_ref"), g("n_rev_ref"), g("f_fwd"), g("f_rev"), g("z"), g("y_sum_total"), g("keep"),
             g("tax_id"), g("n_alignments"), g("first_row"), g("k"), g("N"), g("noise"), int(outs["k"].shape[0]), C.byref(n_tax)))
         return n_tax.value
+
+    # ------------------------------------------------------------------ K1d (C8)
+    def counts_order(self, tax_id_row, z_row, keep_row, first_row, tax_order):
+        """Row permutation of counts.py:167-172 on host arrays: source row of every output row (kept rows only)."""
+        tax_id_row = np.ascontiguousarray(tax_id_row, dtype=np.int64)
+        z_row = np.ascontiguousarray(z_row, dtype=np.int8)
+        keep_row = None if keep_row is None else np.ascontiguousarray(keep_row, dtype=np.uint8)
+        first_row = np.ascontiguousarray(first_row, dtype=np.int64)
+        tax_order = np.ascontiguousarray(tax_order, dtype=np.int64)
+        cap = len(tax_id_row) if keep_row is None else int(np.count_nonzero(keep_row))
+        perm = np.empty(cap, np.int64)
+        n_out = C.c_int64(0)
+        _lib.check(self._lib.mdg_counts_order(self._h, MDG_HOST, len(tax_id_row), ptr(tax_id_row), ptr(z_row), ptr(keep_row), len(first_row),
+                                              ptr(first_row), ptr(tax_order), ptr(perm), cap, C.byref(n_out)))
+        return perm[: n_out.value]
+
+    def counts_order_device(self, cols, outs, n_tax, tax_order, out_perm):
+        """K1d on torch CUDA tensors (`cols` / `outs` of counts_reduce_device; tax_order, out_perm: int64 CUDA tensors).
+        Returns the number of kept rows written to out_perm."""
+        n_out = C.c_int64(0)
+        _lib.check(self._lib.mdg_counts_order(self._h, MDG_DEVICE, cols["tax_id"].numel(), _dptr(cols["tax_id"]), _dptr(outs["z"]),
+                                              _dptr(outs.get("keep")), int(n_tax), _dptr(outs["first_row"]), _dptr(tax_order),
+                                              _dptr(out_perm), out_perm.numel(), C.byref(n_out)))
+        return n_out.value
 
     # ------------------------------------------------------------------ K8 (N3)
     def select_top(self, tax_id_row, n_alignments_row, keep_row, tax_id, first_row, n_top, want_weight=False):

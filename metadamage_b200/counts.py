@@ -82,30 +82,35 @@ def reference_row_order(n_alignments, tax_id, z):
     return np.lexsort((-order, -tax_id.astype(np.int64), -n_alignments.astype(np.int64)))
 
 
+def _decode_spans(text, spans):
+    """(offset, length) byte spans -> list of str, decoding each distinct byte string once."""
+    cache, out = {}, []
+    for o, n in spans:
+        b = text[int(o):int(o) + int(n)]
+        v = cache.get(b)
+        if v is None:
+            v = cache[b] = b.decode("utf-8", "replace")
+        out.append(v)
+    return out
+
+
 def read_mismatch_table_gpu(filename, ctx):
     """Same table as `read_mismatch_table`, with the numeric columns tokenised on the GPU
     (mdg_tsv_parse, K0) instead of by pandas; the two string columns of the 22-column layout are
-    cut out of the file bytes through the (offset, length) spans the kernel returns."""
+    cut out of the file bytes through the (offset, length) spans the kernel returns, decoded once per
+    run of equal spans' bytes (rows of a TaxID share name and rank)."""
     with open(filename, "rb") as fh:
         text = fh.read()
     r = ctx.tsv_parse(text, want_spans=True)
     logger.info("tsv: %d bytes -> %d rows (parse kernels %.3f ms)", len(text), r["n_rows"], ctx.timings()["counts_ms"])
     data = {"tax_id": r["tax_id"]}
-    if r["n_cols"] == 22:
+    n = r["n_rows"]
+    if r["n_cols"] == 22 and n:
+        tax = r["tax_id"]
+        heads = np.flatnonzero(np.r_[True, tax[1:] != tax[:-1]])
+        seg = np.diff(np.r_[heads, n])
         for col, key in (("tax_name", "name_span"), ("tax_rank", "rank_span")):
-            spans = r[key]
-            # few distinct strings, many rows: decode each distinct (offset-independent) value once
-            uniq, inv = np.unique(spans[:, 1], return_inverse=True) if len(spans) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
-            vals = np.empty(len(spans), dtype=object)
-            cache = {}
-            for i in range(len(spans)):
-                o, n = int(spans[i, 0]), int(spans[i, 1])
-                b = text[o:o + n]
-                v = cache.get(b)
-                if v is None:
-                    v = cache[b] = b.decode("utf-8", "replace")
-                vals[i] = v
-            data[col] = vals
+            data[col] = np.repeat(np.array(_decode_spans(text, r[key][heads]), dtype=object), seg)
     else:
         data["tax_name"] = ""
         data["tax_rank"] = ""
@@ -118,11 +123,176 @@ def read_mismatch_table_gpu(filename, ctx):
     return df
 
 
+def split_text_at_taxid_boundaries(text, n_parts):
+    """Cut the file bytes into <= n_parts pieces whose first line starts a new TaxID (K1 is
+    partitioned at segment boundaries, so no TaxID spans two GPUs and nothing is exchanged). A nominal cut
+    at k/n of the bytes is moved forward to the next line whose first field differs from the line before."""
+    n = len(text)
+    if n_parts <= 1 or n < 1 << 16:
+        return [(0, n)]
+    cuts = [0]
+    for k in range(1, n_parts):
+        pos = text.find(b"\n", max(cuts[-1], (n * k) // n_parts))
+        if pos < 0:
+            break
+        pos += 1
+        prev_start = text.rfind(b"\n", 0, pos - 1) + 1
+        prev_id = text[prev_start:text.find(b"\t", prev_start)]
+        while pos < n:
+            tab = text.find(b"\t", pos)
+            if tab < 0 or text[pos:tab] != prev_id:
+                break
+            nxt = text.find(b"\n", pos)
+            if nxt < 0:
+                pos = n
+                break
+            pos = nxt + 1
+        if pos >= n:
+            break
+        if pos > cuts[-1]:
+            cuts.append(pos)
+    return [(a, b) for a, b in zip(cuts, cuts[1:] + [n]) if b > a]
+
+
+def _counts_piece_on_gpu(ctx, text, cfg):
+    """One piece of the file on one GPU: K0 (text -> device columns) -> K1 (device) -> K1d (row order); only the
+    kept rows (already in the reference's order inside this piece: TaxIDs by N_alignments / tax_id descending) and
+    the per-TaxID arrays come back to the host. Returns None if the rows of a TaxID are not contiguous."""
+    import torch
+
+    fwd, rev = cfg.substitution_bases_forward, cfg.substitution_bases_reverse
+    P = int(cfg.max_position)
+    cols, n, n_cols = ctx.tsv_parse_device(text, want_spans=True)
+    t_parse = ctx.timings()["counts_ms"]
+    if n == 0:
+        return dict(n_rows=0, n_cols=n_cols)
+    dev = cols["tax_id"].device
+    tax_all = cols["tax_id"].cpu().numpy()
+    heads = np.flatnonzero(np.r_[True, tax_all[1:] != tax_all[:-1]])
+    if len(np.unique(tax_all[heads])) != len(heads):
+        return None
+    m_cap = len(heads)
+    outs = dict(
+        n_fwd_ref=torch.empty(n, dtype=torch.int32, device=dev), n_rev_ref=torch.empty(n, dtype=torch.int32, device=dev),
+        f_fwd=torch.empty(n, dtype=torch.float32, device=dev), f_rev=torch.empty(n, dtype=torch.float32, device=dev),
+        z=torch.empty(n, dtype=torch.int8, device=dev), y_sum_total=torch.empty(n, dtype=torch.int64, device=dev),
+        keep=torch.empty(n, dtype=torch.uint8, device=dev), tax_id=torch.empty(m_cap, dtype=torch.int64, device=dev),
+        n_alignments=torch.empty(m_cap, dtype=torch.int32, device=dev), first_row=torch.empty(m_cap, dtype=torch.int64, device=dev),
+        k=torch.empty((m_cap, 2 * P), dtype=torch.int32, device=dev), N=torch.empty((m_cap, 2 * P), dtype=torch.int32, device=dev),
+        noise=torch.empty((m_cap, 3), dtype=torch.float64, device=dev))
+    n_tax = ctx.counts_reduce_device(cols, outs, fwd=fwd, rev=rev, max_position=P, min_alignments=cfg.min_alignments,
+                                     min_y_sum=cfg.min_y_sum)
+    t_counts = ctx.timings()["counts_ms"]
+    logger.info("counts: %d rows -> %d TaxIDs kept (K0 %.3f ms, K1 %.3f ms)", n, n_tax, t_parse, t_counts)
+    tax = dict(tax_id=outs["tax_id"][:n_tax].cpu().numpy(), n_alignments=outs["n_alignments"][:n_tax].cpu().numpy().view(np.uint32),
+               first_row=outs["first_row"][:n_tax].cpu().numpy(), k=outs["k"][:n_tax].cpu().numpy().view(np.uint32),
+               N=outs["N"][:n_tax].cpu().numpy().view(np.uint32), noise=outs["noise"][:n_tax].cpu().numpy())
+    # C8: TaxID-level keys sorted on the host (n_tax of them), row-level permutation on the device
+    tax_order = np.lexsort((-tax["tax_id"], -tax["n_alignments"].astype(np.int64)))
+    n_keep = int(torch.count_nonzero(outs["keep"]).item()) if n_tax else 0
+    perm = torch.empty(max(n_keep, 1), dtype=torch.int64, device=dev)
+    n_out = ctx.counts_order_device(cols, outs, n_tax, torch.from_numpy(tax_order).to(dev), perm) if n_tax else 0
+    perm = perm[:n_out]
+
+    def take(t):  # kept rows in output order, to the host
+        return t.index_select(0, perm).cpu().numpy()
+
+    rows = dict(tax_id=take(cols["tax_id"]), n_alignments=take(cols["n_alignments"]).view(np.uint32),
+                is_reverse=take(cols["is_reverse"]), z=take(outs["z"]),
+                counts16=cols["counts16"].index_select(1, perm).cpu().numpy().view(np.uint32),
+                n_fwd_ref=take(outs["n_fwd_ref"]).view(np.uint32), n_rev_ref=take(outs["n_rev_ref"]).view(np.uint32),
+                f_fwd=take(outs["f_fwd"]), f_rev=take(outs["f_rev"]), y_sum_total=take(outs["y_sum_total"]).view(np.uint64))
+    names = ranks = None
+    if n_cols == 22 and n_tax:
+        first = torch.from_numpy(tax["first_row"]).to(dev)
+        names = _decode_spans(text, cols["name_span"].index_select(0, first).cpu().numpy())
+        ranks = _decode_spans(text, cols["rank_span"].index_select(0, first).cpu().numpy())
+    return dict(n_rows=n, n_cols=n_cols, rows=rows, tax=tax, tax_order=tax_order, names=names, ranks=ranks)
+
+
+def _categorical_from_groups(values_per_group, group_of_row):
+    uniq, inv = np.unique(np.asarray(values_per_group, dtype=object), return_inverse=True)
+    return pd.Categorical.from_codes(inv[group_of_row], categories=uniq)
+
+
+def _assemble_df_counts(pieces, cfg):
+    """The kept rows of every piece -> df_counts in the reference's order, columns and dtypes (counts.py:167-172,
+    270-272). Pieces are internally ordered already; a k-way merge by (N_alignments, tax_id) descending joins them."""
+    fwd, rev = cfg.substitution_bases_forward, cfg.substitution_bases_reverse
+    P = int(cfg.max_position)
+    rows = {key: np.concatenate([p["rows"][key] for p in pieces], axis=1 if key == "counts16" else 0) for key in pieces[0]["rows"]}
+    tax = {key: np.concatenate([p["tax"][key][p["tax_order"]] for p in pieces]) for key in pieces[0]["tax"] if key != "first_row"}
+    # rows per kept TaxID, in each piece's output order
+    seg_len = np.concatenate([np.diff(np.r_[np.flatnonzero(np.r_[True, p["rows"]["tax_id"][1:] != p["rows"]["tax_id"][:-1]]),
+                                            len(p["rows"]["tax_id"])]) if len(p["rows"]["tax_id"]) else np.zeros(0, np.int64)
+                              for p in pieces]).astype(np.int64)
+    names = [v for p in pieces for v in (np.asarray(p["names"], dtype=object)[p["tax_order"]] if p["names"] is not None else [""] * len(p["tax_order"]))]
+    ranks = [v for p in pieces for v in (np.asarray(p["ranks"], dtype=object)[p["tax_order"]] if p["ranks"] is not None else [""] * len(p["tax_order"]))]
+    if len(pieces) > 1:  # merge the pieces' TaxID lists; rows follow their TaxIDs
+        order = np.lexsort((-tax["tax_id"], -tax["n_alignments"].astype(np.int64)))
+        starts = np.r_[0, np.cumsum(seg_len)[:-1]]
+        row_idx = np.concatenate([np.arange(starts[t], starts[t] + seg_len[t]) for t in order]) if len(order) else np.zeros(0, np.int64)
+        rows = {key: (val[:, row_idx] if key == "counts16" else val[row_idx]) for key, val in rows.items()}
+        tax = {key: val[order] for key, val in tax.items()}
+        seg_len = seg_len[order]
+        names = [names[t] for t in order]
+        ranks = [ranks[t] for t in order]
+    n_tax = len(seg_len)
+    group_of_row = np.repeat(np.arange(n_tax), seg_len)
+    data = {"tax_id": rows["tax_id"], "tax_name": _categorical_from_groups(names, group_of_row) if n_tax else [],
+            "tax_rank": _categorical_from_groups(ranks, group_of_row) if n_tax else [], "N_alignments": rows["n_alignments"],
+            "strand": np.where(rows["is_reverse"] == 1, "3'", "5'"), "position": rows["z"]}
+    for i, name in enumerate(REF_OBS_BASES):
+        data[name] = rows["counts16"][i]
+    # the reference's column layout (counts.py:88, 111, 201-203): a reference-base column shared by both
+    # substitutions is written once
+    data[fwd[0]] = rows["n_fwd_ref"]
+    data[rev[0]] = rows["n_rev_ref"]
+    data[f"f_{fwd}"] = rows["f_fwd"]
+    data[f"f_{rev}"] = rows["f_rev"]
+    data["y_sum_total"] = rows["y_sum_total"]
+    df = pd.DataFrame(data)
+    df["shortname"] = cfg.shortname
+    df = utils.downcast_dataframe(df, ["tax_id", "tax_name", "tax_rank", "strand", "shortname"])
+    # K1's dense per-TaxID outputs are remembered for this very DataFrame object (df_counts order), so that
+    # compute_fits does not rebuild them from the rows
+    first_row = np.r_[0, np.cumsum(seg_len)[:-1]].astype(np.int64) if n_tax else np.zeros(0, np.int64)
+    _remember_dense(df, dict(tax_id=tax["tax_id"], tax_name=np.asarray(names, dtype=object), tax_rank=np.asarray(ranks, dtype=object),
+                             N_alignments=tax["n_alignments"], k=tax["k"], N=tax["N"], noise=tax["noise"], mism12=None,
+                             first_row=first_row, max_position=P, fwd=fwd, rev=rev))
+    return df
+
+
 def compute_counts(cfg, df_in=None, ctx=None):
-    """The GPU replacement of compute_counts_with_dask (counts.py:212-273)."""
-    ctx = ctx or get_context(0)
+    """The GPU replacement of compute_counts_with_dask (counts.py:212-273): file bytes -> K0 -> K1 -> K1d on the
+    device(s), only the kept rows return to the host. With cfg.gpus > 1 the file is cut at TaxID boundaries and
+    every GPU handles one piece (no exchange)."""
     if df_in is None:
-        df_in = read_mismatch_table_gpu(cfg.filename, ctx)
+        with open(cfg.filename, "rb") as fh:
+            text = fh.read()
+        n_gpus = max(1, min(int(getattr(cfg, "gpus", 1) or 1), _lib_device_count()))
+        spans = split_text_at_taxid_boundaries(text, n_gpus) if ctx is None else [(0, len(text))]
+        from .parallel import run_on_gpus
+
+        def worker(rank, start, stop):
+            out = []
+            for a, b in spans[start:stop]:
+                out.append(_counts_piece_on_gpu(ctx or get_context(rank), text[a:b] if (a, b) != (0, len(text)) else text, cfg))
+            return out
+
+        pieces = [p for part in run_on_gpus(len(spans), len(spans), worker) if part for p in part]
+        if all(p is not None for p in pieces):
+            pieces = [p for p in pieces if p.get("n_rows", 0) > 0 and len(p["rows"]["tax_id"]) >= 0]
+            if pieces and len({p["n_cols"] for p in pieces}) == 1:
+                tids = np.concatenate([p["tax"]["tax_id"] for p in pieces])
+                if len(np.unique(tids)) == len(tids):
+                    return _assemble_df_counts(pieces, cfg)
+            if not pieces:
+                df_in = read_mismatch_table_gpu(cfg.filename, ctx or get_context(0))
+        # rows of a TaxID are not contiguous (or the pieces disagree): regroup on the host and take the host-buffer path
+        if df_in is None:
+            df_in = read_mismatch_table_gpu(cfg.filename, ctx or get_context(0))
+    ctx = ctx or get_context(0)
     df_in = group_rows_by_tax_id(df_in)
     fwd, rev = cfg.substitution_bases_forward, cfg.substitution_bases_reverse
     cols = soa_columns(df_in)
@@ -138,10 +308,19 @@ def compute_counts(cfg, df_in=None, ctx=None):
     df[f"f_{fwd}"] = r["f_fwd"][keep]
     df[f"f_{rev}"] = r["f_rev"][keep]
     df["y_sum_total"] = r["y_sum_total"][keep]
-    order = reference_row_order(df["N_alignments"].to_numpy(), df["tax_id"].to_numpy(), df["position"].to_numpy())
-    df = df.iloc[order].reset_index(drop=True)
+    tax_order = np.lexsort((-r["tax_id"], -r["n_alignments"].astype(np.int64)))
+    order = ctx.counts_order(cols["tax_id"], r["z"], r["keep"], r["first_row"], tax_order) if r["n_tax"] else np.zeros(0, np.int64)
+    # `order` indexes input rows; df holds the kept rows only
+    kept_pos = np.cumsum(keep) - 1
+    df = df.iloc[kept_pos[order]].reset_index(drop=True)
     df["shortname"] = cfg.shortname
     return utils.downcast_dataframe(df, ["tax_id", "tax_name", "tax_rank", "strand", "shortname"])
+
+
+def _lib_device_count():
+    from . import _lib
+
+    return _lib.load().mdg_device_count() or 1
 
 
 # the reference's name for the seam (counts.py:212); `use_processes` is accepted and ignored
@@ -170,30 +349,46 @@ def load_counts(cfg):
     return df_counts
 
 
-def dense_from_df_counts(df_counts, cfg):
-    """df_counts (reference order: per TaxID z = +1..+P then -1..-P) -> tax ids, names, ranks,
-    N_alignments and the dense k/N [n_tax][2P] + mism12 [n_tax][2P][12] the fit kernels take
-    (fits.py:398-419, 359-363). Missing positions stay zero."""
+_DENSE = {}
+
+
+def _remember_dense(df, dense):
+    import weakref
+
+    key = id(df)
+    _DENSE[key] = dense
+    weakref.finalize(df, _DENSE.pop, key, None)
+
+
+def dense_from_df_counts(df_counts, cfg, ctx=None):
+    """df_counts -> what the fit kernels take (fits.py:398-419, 359-376): tax ids, names, ranks, N_alignments in
+    df_counts order, dense k/N [n_tax][2P] and the noise statistic [n_tax][3]. If this DataFrame came out of
+    `compute_counts` in this process, K1 has produced all of that already; otherwise (parquet cache, a filtered
+    frame) K1 runs once more on the frame's own columns with the cuts switched off. Rows with |z| > max_position
+    are ignored; missing positions stay zero."""
     P = int(cfg.max_position)
     fwd, rev = cfg.substitution_bases_forward, cfg.substitution_bases_reverse
+    hit = _DENSE.get(id(df_counts))
+    if hit is not None and hit["max_position"] == P and hit["fwd"] == fwd and hit["rev"] == rev and \
+            int(hit["first_row"][-1] if len(hit["first_row"]) else 0) <= len(df_counts):
+        return hit
+    ctx = ctx or get_context(0)
+    n = len(df_counts)
     tax = df_counts["tax_id"].to_numpy(np.int64)
-    uniq, first, inv = np.unique(tax, return_index=True, return_inverse=True)
-    rank_of = np.argsort(np.argsort(first))      # order of first appearance (df_counts order)
-    t_idx = rank_of[inv]
-    n_tax = len(uniq)
+    if n == 0:
+        z0 = np.zeros((0, 2 * P), np.uint32)
+        return dict(tax_id=tax, tax_name=np.zeros(0, object), tax_rank=np.zeros(0, object), N_alignments=np.zeros(0, np.uint32),
+                    k=z0, N=z0.copy(), noise=np.zeros((0, 3)), mism12=None, first_row=np.zeros(0, np.int64), max_position=P, fwd=fwd, rev=rev)
     z = df_counts["position"].to_numpy(np.int64)
-    ok = np.abs(z) <= P
-    slot = np.where(z > 0, z - 1, P + np.abs(z) - 1)
-    k = np.zeros((n_tax, 2 * P), np.uint32)
-    N = np.zeros((n_tax, 2 * P), np.uint32)
-    kcol = np.where(z > 0, df_counts[fwd].to_numpy(np.int64), df_counts[rev].to_numpy(np.int64))
-    ncol = np.where(z > 0, df_counts[fwd[0]].to_numpy(np.int64), df_counts[rev[0]].to_numpy(np.int64))
-    np.add.at(k, (t_idx[ok], slot[ok]), kcol[ok].astype(np.uint32))
-    np.add.at(N, (t_idx[ok], slot[ok]), ncol[ok].astype(np.uint32))
-    off = [c for c in REF_OBS_BASES if c[0] != c[1]]
-    m12 = np.zeros((n_tax, 2 * P, 12), np.uint32)
-    np.add.at(m12, (t_idx[ok], slot[ok]), df_counts[off].to_numpy(np.uint32)[ok])
-    head = np.sort(first)
-    meta = df_counts.iloc[head]
-    return dict(tax_id=tax[head], tax_name=meta["tax_name"].to_numpy(), tax_rank=meta["tax_rank"].to_numpy(),
-                N_alignments=meta["N_alignments"].to_numpy(np.uint32), k=k, N=N, mism12=m12)
+    pos0 = np.clip(np.abs(z) - 1, 0, 254).astype(np.uint8)
+    strand = df_counts["strand"]
+    is_rev = (strand.astype(object).to_numpy() != "5'").astype(np.uint8) if "strand" in df_counts else (z < 0).astype(np.uint8)
+    c16 = np.ascontiguousarray(df_counts[REF_OBS_BASES].to_numpy(np.uint32).T)
+    r = ctx.counts_reduce(tax, df_counts["N_alignments"].to_numpy(np.uint32), is_rev, pos0, c16, fwd=fwd, rev=rev,
+                          max_position=P, min_alignments=0, min_y_sum=0, want_noise=True, want_rows=False)
+    if len(np.unique(r["tax_id"])) != r["n_tax"]:
+        raise ValueError("df_counts: the rows of a TaxID must be contiguous")
+    meta = df_counts.iloc[r["first_row"]]
+    return dict(tax_id=r["tax_id"], tax_name=meta["tax_name"].astype(object).to_numpy(), tax_rank=meta["tax_rank"].astype(object).to_numpy(),
+                N_alignments=r["n_alignments"], k=r["k"], N=r["N"], noise=r["noise"], mism12=None, first_row=r["first_row"],
+                max_position=P, fwd=fwd, rev=rev)

@@ -615,6 +615,87 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1d: row order of df_counts
+// ---------------------------------------------------------------------------------------------
+int mdg_counts_order(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_id_row, const int8_t* z_row, const uint8_t* keep_row,
+                     int64_t n_tax, const int64_t* first_row, const int64_t* tax_order, int64_t* out_perm, int64_t perm_capacity,
+                     int64_t* out_n_rows) {
+    if (!ctx) { set_error("ctx is NULL"); return MDG_ERR_INVALID; }
+    if (n_rows < 0 || n_tax < 0 || perm_capacity < 0 || !out_n_rows || (mem != MDG_HOST && mem != MDG_DEVICE) ||
+        (n_tax > 0 && (!tax_id_row || !z_row || !first_row || !tax_order || !out_perm || n_rows <= 0))) {
+        set_error("mdg_counts_order: invalid argument");
+        return MDG_ERR_INVALID;
+    }
+    *out_n_rows = 0;
+    ctx->timings = mdg_timings{};
+    if (n_tax == 0) return MDG_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const bool host = (mem == MDG_HOST);
+    const size_t nr = (size_t)n_rows, nt = (size_t)n_tax;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    int rc;
+    OrderLaunch ol = {};
+    ol.n_rows = n_rows; ol.n_tax = n_tax;
+    ol.tax_id_row = reinterpret_cast<const long long*>(tax_id_row); ol.z_row = z_row; ol.keep_row = keep_row;
+    ol.first_row = reinterpret_cast<const long long*>(first_row); ol.tax_order = reinterpret_cast<const long long*>(tax_order);
+    ol.perm = reinterpret_cast<long long*>(out_perm);
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+    if (host) {
+        if ((rc = ctx->buf[22].ensure(up(nr * 8) + up(nr) + up(nr) + 2 * up(nt * 8) + up((size_t)perm_capacity * 8)))) return rc;
+        unsigned char* b = ctx->buf[22].as<unsigned char>();
+        size_t o = 0;
+        auto put = [&](const void* src, size_t bytes) -> void* {
+            void* d = b + o; o += up(bytes);
+            if (src) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+            return d;
+        };
+        ol.tax_id_row = (const long long*)put(tax_id_row, nr * 8);
+        ol.z_row = (const int8_t*)put(z_row, nr);
+        void* kp = put(keep_row, nr);
+        ol.keep_row = keep_row ? (const uint8_t*)kp : nullptr;
+        ol.first_row = (const long long*)put(first_row, nt * 8);
+        ol.tax_order = (const long long*)put(tax_order, nt * 8);
+        ol.perm = (long long*)put(nullptr, (size_t)perm_capacity * 8);
+        MDG_CUDA_TRY(cudaGetLastError());
+    }
+    if ((rc = ctx->buf[23].ensure(up(nt * 4) + up(nt * 8) + 256))) return rc;
+    unsigned char* sb = ctx->buf[23].as<unsigned char>();
+    ol.len_sorted = reinterpret_cast<int*>(sb);
+    long long* d_start = reinterpret_cast<long long*>(sb + up(nt * 4));
+    long long* d_total = reinterpret_cast<long long*>(sb + up(nt * 4) + up(nt * 8));
+    ol.out_start = d_start;
+    ol.error_flag = reinterpret_cast<int*>(d_total + 1);
+    MDG_CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, st));
+    const unsigned grid = (unsigned)((n_tax + kOrderWarps - 1) / kOrderWarps);
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+    counts_order_kernel<0><<<grid, kOrderWarps * 32, 0, st>>>(ol);
+    counts_scan_kernel<<<1, 1024, 0, st>>>(ol.len_sorted, n_tax, d_start, d_total);
+    MDG_CUDA_TRY(cudaGetLastError());
+    long long h_total = 0;
+    int h_err = 0;
+    MDG_CUDA_TRY(cudaMemcpyAsync(&h_total, d_total, 8, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaMemcpyAsync(&h_err, ol.error_flag, 4, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_err) { set_error("mdg_counts_order: a TaxID has more than %d rows", MDG_MAX_SEGMENT_ROWS); return MDG_ERR_SEGMENT_TOO_LONG; }
+    if (h_total > perm_capacity) {
+        set_error("mdg_counts_order: %lld kept rows but room for %lld", h_total, (long long)perm_capacity);
+        return MDG_ERR_INVALID;
+    }
+    counts_order_kernel<1><<<grid, kOrderWarps * 32, 0, st>>>(ol);
+    MDG_CUDA_TRY(cudaGetLastError());
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+    ctx->timings.n_launches = 3;
+    if (host && h_total > 0) MDG_CUDA_TRY(cudaMemcpyAsync(out_perm, ol.perm, (size_t)h_total * 8, cudaMemcpyDeviceToHost, st));
+    MDG_CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+    MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->timings.counts_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+    ctx->timings.total_ms = elapsed(ctx->ev[0], ctx->ev[3]);
+    *out_n_rows = h_total;
+    return MDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K0
 // ---------------------------------------------------------------------------------------------
 int mdg_tsv_parse(mdg_ctx* ctx, int mem, const char* text, int64_t n_bytes, int64_t capacity, int64_t* tax_id,

@@ -541,4 +541,75 @@ __global__ void __launch_bounds__(128) counts_permute_kernel(const CountsPermute
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1d: row order of df_counts (counts.py:167-172 sort_by_alignments): TaxIDs by N_alignments descending, then
+// tax_id descending (a sort of n_tax keys, done by the caller), and inside a TaxID the kept rows by
+// z = +1..+P, -1..-P (sort key 1/z for z > 0 else z, descending; stable). The row-level part — one
+// destination per kept row, O(rows) — is these two kernels: one warp per TaxID of the OUTPUT order.
+// ---------------------------------------------------------------------------------------------
+struct OrderLaunch {
+    long long n_rows;
+    const long long* tax_id_row;
+    const int8_t* z_row;
+    const uint8_t* keep_row;     // NULL: every row is kept
+    long long n_tax;
+    const long long* first_row;  // [n_tax] first row of every kept TaxID (input order)
+    const long long* tax_order;  // [n_tax] index (into first_row) of the TaxID that comes i-th in the output
+    int* len_sorted;             // [n_tax] kept rows of the i-th TaxID of the output
+    const long long* out_start;  // [n_tax] exclusive scan of len_sorted
+    long long* perm;             // [kept rows] source row of every output row
+    int* error_flag;
+};
+
+constexpr int kOrderWarps = 4;
+
+// rank key of a signed 1-indexed position: +1, +2, ..., then -1, -2, ...
+__device__ __forceinline__ int order_zslot(int z) { return z > 0 ? z - 1 : 128 - z - 1; }
+
+template <int PASS>
+__global__ void __launch_bounds__(kOrderWarps * 32) counts_order_kernel(const OrderLaunch p) {
+    __shared__ short s_key[kOrderWarps][MDG_MAX_SEGMENT_ROWS];  // zslot of the kept rows, -1 for dropped rows
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * kOrderWarps + warp;
+    if (i >= p.n_tax) return;
+    const long long r0 = p.first_row[p.tax_order[i]];
+    const long long tid = p.tax_id_row[r0];
+    // segment length: rows of a TaxID are contiguous
+    int L = 0;
+    for (int base = 0; base < MDG_MAX_SEGMENT_ROWS; base += 32) {
+        const long long r = r0 + base + lane;
+        const bool same = r < p.n_rows && p.tax_id_row[r] == tid;
+        const unsigned m = __ballot_sync(0xffffffffu, same);
+        if (m != 0xffffffffu) { L = base + __ffs(~m) - 1; break; }
+        L = base + 32;
+    }
+    if (L >= MDG_MAX_SEGMENT_ROWS && r0 + L < p.n_rows && p.tax_id_row[r0 + L] == tid) {
+        if (lane == 0) atomicMax(p.error_flag, 1);
+        return;
+    }
+    int kept = 0;
+    for (int j = lane; j < L; j += 32) {
+        const bool k = p.keep_row == nullptr || p.keep_row[r0 + j] != 0;
+        s_key[warp][j] = k ? (short)order_zslot((int)p.z_row[r0 + j]) : (short)-1;
+        kept += k;
+    }
+    __syncwarp();
+    if (PASS == 0) {
+        kept = __reduce_add_sync(0xffffffffu, kept);
+        if (lane == 0) p.len_sorted[i] = kept;
+    } else {
+        const long long base = p.out_start[i];
+        for (int j = lane; j < L; j += 32) {
+            const int kj = s_key[warp][j];
+            if (kj < 0) continue;
+            int rank = 0;
+            for (int m = 0; m < L; ++m) {
+                const int km = s_key[warp][m];
+                rank += (km >= 0) && (km < kj || (km == kj && m < j));
+            }
+            p.perm[base + rank] = r0 + j;
+        }
+    }
+}
+
 }  // namespace mdg

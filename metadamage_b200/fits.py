@@ -69,15 +69,39 @@ def get_top_max_fits(df_counts, n_fits):
 def fit_dense(dense, cfg, fit_cfg, n_gpus=1):
     """Run mdg_fit_batch over `n_gpus` contiguous shares of the dense batch; host-side concat."""
     n_tax = len(dense["tax_id"])
+    R = dense["k"].shape[1]
+    if n_tax == 0:
+        from ._abi import FIT_RESULT_DTYPE
+
+        e = np.zeros((0, R), np.float32)
+        return dict(result=np.zeros(0, FIT_RESULT_DTYPE), median=e, hpdi_lo=e.copy(), hpdi_hi=e.copy())
     n_dev = max(1, min(int(n_gpus), _lib.load().mdg_device_count() or 1))
 
     def worker(rank, start, stop):
         sl = slice(start, stop)
         return _context(rank).fit_batch(dense["tax_id"][sl], dense["k"][sl], dense["N"][sl], fit_cfg,
-                                        mism12=dense["mism12"][sl] if dense.get("mism12") is not None else None)
+                                        mism12=dense["mism12"][sl] if dense.get("mism12") is not None else None,
+                                        noise3=dense["noise"][sl] if dense.get("noise") is not None else None)
 
     parts = [p for p in run_on_gpus(n_tax, n_dev, worker) if p is not None]
     return {key: np.concatenate([p[key] for p in parts]) for key in ("result", "median", "hpdi_lo", "hpdi_hi")}
+
+
+def select_top_dense(df_counts, dense, n_fits, ctx=None):
+    """`--max-fits` on the device (mdg_select_top, K8): fits.py:736-744 on the arrays instead of the pandas
+    groupby / nlargest / isin (kept as `extract_top_max_fits`, the test oracle): the n_fits TaxIDs with the largest
+    sum of N_alignments over their rows, ties to the smaller tax id, in df_counts order."""
+    n_tax = len(dense["tax_id"])
+    if n_fits is None or n_fits <= 0 or n_fits >= n_tax:
+        return dense
+    ctx = ctx or _context(0)
+    idx = ctx.select_top(df_counts["tax_id"].to_numpy(np.int64), df_counts["N_alignments"].to_numpy(np.uint32), None,
+                         dense["tax_id"], dense["first_row"], int(n_fits))
+    out = dict(dense)
+    for key in ("tax_id", "tax_name", "tax_rank", "N_alignments", "k", "N", "noise", "mism12", "first_row"):
+        if out.get(key) is not None:
+            out[key] = out[key][idx]
+    return out
 
 
 def make_df_fit_results(res, dense, cfg):
@@ -123,9 +147,10 @@ def make_df_fit_map(res, dense, ok, cfg):
     return utils.downcast_dataframe(df, ["tax_id", "shortname"])
 
 
-def compute_fits(df_counts, cfg, mcmc_kwargs=None, return_map=False):
-    """The GPU replacement of fits.compute_fits (fits.py:709-730)."""
-    dense = dense_from_df_counts(df_counts, cfg)
+def compute_fits(df_counts, cfg, mcmc_kwargs=None, return_map=False, n_fits=None):
+    """The GPU replacement of fits.compute_fits (fits.py:709-730). `n_fits`: fit only the top TaxIDs of
+    fits.py:736-744 (what get_fits does by filtering the frame first), selected on the device."""
+    dense = select_top_dense(df_counts, dense_from_df_counts(df_counts, cfg), n_fits)
     fit_cfg = fit_config_from(cfg, mcmc_kwargs)
     out = fit_dense(dense, cfg, fit_cfg, n_gpus=getattr(cfg, "gpus", 1))
     df_fit_results, ok = make_df_fit_results(out["result"], dense, cfg)
@@ -150,8 +175,8 @@ def get_fits(df_counts, cfg):
             logger.info("Fit: Loading fits from parquet-file.")
             return pq_results.load(), pq_predictions.load()
     logger.info("Fit: Generating fits and saving to file.")
-    df_top = get_top_max_fits(df_counts, cfg.N_fits)
-    df_fit_results, df_fit_predictions, df_fit_map = compute_fits(df_top, cfg, mcmc_kwargs_default(), return_map=True)
+    df_fit_results, df_fit_predictions, df_fit_map = compute_fits(df_counts, cfg, mcmc_kwargs_default(), return_map=True,
+                                                                  n_fits=cfg.N_fits)
     meta = cfg.to_dict()
     pq_results.save(df_fit_results, metadata=meta)
     pq_predictions.save(df_fit_predictions, metadata=meta)

@@ -171,20 +171,31 @@ def fake_df_counts(sample, cfg):
     return df
 
 
+def dense_by_oracle(s, oracle):
+    """What counts.dense_from_df_counts returns (it needs the GPU: K1 on the frame's columns), built from the oracle."""
+    r = oracle.counts_reduce(s["tax_id"], s["n_alignments"], s["is_reverse"], s["pos0"], s["counts16"])
+    n = r["n_tax"]
+    return dict(tax_id=r["tax_id"], tax_name=np.array([""] * n, dtype=object), tax_rank=np.array([""] * n, dtype=object),
+                N_alignments=r["n_alignments"], k=r["k"], N=r["N"], noise=r["noise"], mism12=None, first_row=r["first_row"],
+                max_position=15, fwd="CT", rev="GA")
+
+
+@pytest.mark.gpu
 def test_dense_from_df_counts(tmp_path, sample_inputs, oracle):
+    """K1 on a df_counts frame's own columns (the parquet-cache path of compute_fits) == the oracle's dense k/N/noise."""
     cfg = make_cfg(tmp_path)
     s = sample_inputs["ancient"]
     dense = counts.dense_from_df_counts(fake_df_counts(s, cfg), cfg)
     r = oracle.counts_reduce(s["tax_id"], s["n_alignments"], s["is_reverse"], s["pos0"], s["counts16"])
     assert np.array_equal(dense["k"], r["k"]) and np.array_equal(dense["N"], r["N"])
-    assert list(dense["tax_id"]) == [0, 1, 2] and dense["mism12"].shape == (3, 30, 12)
-    assert dense["mism12"][0, 0, 5] == s["counts16"][7, 0]  # CT at z = +1
+    assert list(dense["tax_id"]) == [0, 1, 2] and dense["mism12"] is None
+    np.testing.assert_allclose(dense["noise"], r["noise"], rtol=1e-11)
 
 
-def test_fit_dataframes_have_reference_schema(tmp_path, sample_inputs):
+def test_fit_dataframes_have_reference_schema(tmp_path, sample_inputs, oracle):
     cfg = make_cfg(tmp_path)
     cfg.add_filename("data_ancient.txt")
-    dense = counts.dense_from_df_counts(fake_df_counts(sample_inputs["ancient"], cfg), cfg)
+    dense = dense_by_oracle(sample_inputs["ancient"], oracle)
     res = np.zeros(3, dtype=FIT_RESULT_DTYPE)
     res["tax_id"] = dense["tax_id"]
     res["D_max"] = [0.4, 0.41, 0.42]
@@ -239,3 +250,28 @@ def test_bench_reference_arm_prints_one_json_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_split_text_at_taxid_boundaries():
+    """The multi-GPU counts stage cuts the file where a new TaxID starts (no TaxID spans two pieces)."""
+    lines = []
+    for t in range(300):
+        for r in range(1 + (t * 7) % 40):
+            lines.append(f"{t * 3 + 1}\tname\trank\t{10 + t}\t5'\t{r}" + "\t1" * 16)
+    text = ("\n".join(lines) + "\n").encode() * 1
+    text = text * 1
+    for n_parts in (1, 2, 3, 8):
+        spans = counts.split_text_at_taxid_boundaries(text * 4 if False else text, n_parts)
+        assert spans[0][0] == 0 and spans[-1][1] == len(text)
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        seen = []
+        for a, b in spans:
+            assert a == 0 or text[a - 1:a] == b"\n"
+            ids = [ln.split(b"\t")[0] for ln in text[a:b].splitlines()]
+            runs = [ids[i] for i in range(len(ids)) if i == 0 or ids[i] != ids[i - 1]]
+            seen.append(set(runs))
+        for i in range(len(seen)):
+            for j in range(i + 1, len(seen)):
+                assert not (seen[i] & seen[j])
+    big = text * 3  # large enough to be cut
+    assert len(counts.split_text_at_taxid_boundaries(big, 4)) >= 2

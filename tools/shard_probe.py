@@ -23,7 +23,7 @@ cfg = _lib.default_config()
 # scheduling variants (environment knobs of mdg_fit_batch), e.g. MDG_PROBE_VARIANTS="MDG_HOLD_AFTER=0;MDG_HOLD_AFTER=48000"
 VARIANTS = [dict(kv.split("=") for kv in v.split(",") if kv) for v in os.environ.get("MDG_PROBE_VARIANTS", "").split(";")] or [{}]
 for rank in range(int(lo), int(hi) + 1):
-    g = bench.workload(args, rank)
+    g = bench.workload(args, rank, 8)
     r = ctx.counts_reduce(g["tax_id"], g["n_alignments"], g["is_reverse"], g["pos0"], g["counts16"], want_noise=True)
     best = None
     for variant in VARIANTS:
