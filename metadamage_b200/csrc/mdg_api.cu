@@ -59,9 +59,9 @@ constexpr int kNumEvents = 16;
 // same batch or of the next submitted batch) starts under the tail of chunk c, which is a handful of long
 // sequential chains on an otherwise idle GPU.
 struct mdg_fit_lane {
-    cudaStream_t main = nullptr, side[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t main = nullptr, side[4] = {nullptr, nullptr, nullptr, nullptr};  // main: high priority; side: the four NUTS launches
     cudaEvent_t ev[5] = {};  // chunk begin, MAP end, NUTS end, predictive end, done (after assembly + D2H)
-    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     mdg::DevBuf rec, map, pred, counters, samples, waic, waic_acc[4];
     unsigned long long* h_leap = nullptr;  // pinned [MDG_NUM_RUNS]
     bool busy = false;
@@ -329,14 +329,21 @@ int mdg_ctx_create(int device, mdg_ctx** out) {
         if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->epoch)) != cudaSuccess) return fail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->inputs_ready, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    // The NUTS launches are persistent and fill every CTA slot of the GPU; the short kernels around them (MAP,
+    // posterior predictive, assembly) of the OTHER batch in flight must not queue behind the NUTS CTAs that are
+    // still waiting for a slot, or a batch could not complete (and the next one not be submitted) before the
+    // following batch's NUTS launches are through: the lane's main stream gets the highest priority, the NUTS
+    // streams the lowest.
+    int prio_low = 0, prio_high = 0;
+    if ((e = cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high)) != cudaSuccess) return fail(e, "cudaDeviceGetStreamPriorityRange");
     for (auto& ln : ctx->lane) {
-        if ((e = cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
-        for (int i = 0; i < 3; ++i)
-            if ((e = cudaStreamCreateWithFlags(&ln.side[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+        if ((e = cudaStreamCreateWithPriority(&ln.main, cudaStreamNonBlocking, prio_high)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+        for (int i = 0; i < 4; ++i)
+            if ((e = cudaStreamCreateWithPriority(&ln.side[i], cudaStreamNonBlocking, prio_low)) != cudaSuccess) return fail(e, "cudaStreamCreate");
         for (int i = 0; i < 5; ++i)
             if ((e = cudaEventCreate(&ln.ev[i])) != cudaSuccess) return fail(e, "cudaEventCreate");
         if ((e = cudaEventCreateWithFlags(&ln.fork_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 4; ++i)
             if ((e = cudaEventCreateWithFlags(&ln.join_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
         if ((e = cudaHostAlloc((void**)&ln.h_leap, MDG_NUM_RUNS * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess)
             return fail(e, "cudaHostAlloc");
@@ -354,7 +361,7 @@ void mdg_ctx_destroy(mdg_ctx* ctx) {
     DeviceGuard guard(ctx->device);
     for (auto& ln : ctx->lane) {
         if (ln.main) cudaStreamSynchronize(ln.main);
-        for (int i = 0; i < 3; ++i) if (ln.side[i]) cudaStreamSynchronize(ln.side[i]);
+        for (int i = 0; i < 4; ++i) if (ln.side[i]) cudaStreamSynchronize(ln.side[i]);
     }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->buf) b.release();
@@ -367,7 +374,7 @@ void mdg_ctx_destroy(mdg_ctx* ctx) {
             b->release();
         for (int i = 0; i < 5; ++i) if (ln.ev[i]) cudaEventDestroy(ln.ev[i]);
         if (ln.fork_ev) cudaEventDestroy(ln.fork_ev);
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             if (ln.join_ev[i]) cudaEventDestroy(ln.join_ev[i]);
             if (ln.side[i]) cudaStreamDestroy(ln.side[i]);
         }
@@ -1117,7 +1124,7 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
         fl.trace = d_trace ? d_trace + (size_t)c0 * MDG_NUM_RUNS * (W + S) * 4 : nullptr;
         for (int r = 0; r < MDG_NUM_RUNS; ++r) fl.sample_slot[r] = out_samples ? r : ((r & 1) ? -1 : r / 2);
         MDG_CUDA_TRY(cudaEventRecord(ln.fork_ev, ls));
-        for (int i = 0; i < 3; ++i) MDG_CUDA_TRY(cudaStreamWaitEvent(ln.side[i], ln.fork_ev, 0));
+        for (int i = 0; i < 4; ++i) MDG_CUDA_TRY(cudaStreamWaitEvent(ln.side[i], ln.fork_ev, 0));
         {
             // Launch order = dispatch order of the persistent CTAs: the kernels share the SMs as CTAs
             // retire, so the whole step behaves like one list schedule over all (TaxID, run) items.
@@ -1138,18 +1145,18 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
             if (v1) {
                 const int npl_half = pack ? 1 : npl_for(P, 32), gw_half = pack ? 16 : 32;
                 if (fwd_rev && (rc = launch_nuts_dispatch<0>(ctx, ln.side[1], c, npl_half, gw_half))) return bail(rc);
-                if ((rc = launch_nuts_dispatch<0>(ctx, ls, a, npl_for(R, 32), 32))) return bail(rc);
+                if ((rc = launch_nuts_dispatch<0>(ctx, ln.side[3], a, npl_for(R, 32), 32))) return bail(rc);
                 if (fwd_rev && (rc = launch_nuts_dispatch<1>(ctx, ln.side[2], d, npl_half, gw_half))) return bail(rc);
                 if ((rc = launch_nuts_dispatch<1>(ctx, ln.side[0], b, npl_for(R, 32), 32))) return bail(rc);
             } else {
                 const int gw_all = env_int("MDG_GW_ALL", 8), gw_half = env_int("MDG_GW_HALF", 8);
                 if (fwd_rev && (rc = launch_nuts_group_dispatch<0>(ctx, ln.side[1], c, ln.waic_acc[2], gw_half))) return bail(rc);
-                if ((rc = launch_nuts_group_dispatch<0>(ctx, ls, a, ln.waic_acc[0], gw_all))) return bail(rc);
+                if ((rc = launch_nuts_group_dispatch<0>(ctx, ln.side[3], a, ln.waic_acc[0], gw_all))) return bail(rc);
                 if (fwd_rev && (rc = launch_nuts_group_dispatch<1>(ctx, ln.side[2], d, ln.waic_acc[3], gw_half))) return bail(rc);
                 if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
             }
         }
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             MDG_CUDA_TRY(cudaEventRecord(ln.join_ev[i], ln.side[i]));
             MDG_CUDA_TRY(cudaStreamWaitEvent(ls, ln.join_ev[i], 0));
         }
