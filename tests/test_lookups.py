@@ -80,6 +80,6 @@ def test_from_fit_rows_without_files():
     med = np.arange(n * 30, dtype=np.float32).reshape(n, 30)
     st = lookups.ResultArrays.from_fit(res, dense, "s1", med, med, med)
     assert st.n == 5 and 12 not in st.categorical["tax_id"].values()
-    assert list(st.select({"N_alignments": (2, 3)})) == [1, 4]            # exponents of ten: 100 .. 1000, the failed fit gone
+    assert list(st.select({"N_alignments": (2, 3)})) == [1, 3, 4]         # exponents of ten: 100 .. 1000, the failed fit gone
     assert list(st.select({"tax_names": ["a", "f"], "n_sigma": (0, 10)})) == [0, 4]
     assert np.array_equal(st.prediction("s1", 13)["median"], med[3])
