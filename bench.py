@@ -341,7 +341,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ctx = Context(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # the ctx stream carries K1 and the copies; like the library's own short-kernel streams it outranks the persistent
+    # NUTS launches of the batch in flight, whose waiting CTAs would otherwise be served first
+    stream = torch.cuda.Stream(dev, priority=-1)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     cfg = _lib.default_config(find_heuristic_step_size=args.heuristic)
     P = args.max_position

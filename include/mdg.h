@@ -94,7 +94,7 @@ typedef struct mdg_fit_config {
                                        * at initialisation and at every adaptation-window end. Default 0 = numpyro 0.4.1's
                                        * default (False), which fits.py:382-387 does not override */
     int32_t reference_quirks;         /* 1: D_max_reverse predictive uses the forward N (fits.py:343-348) */
-    int32_t pack_half_warps;          /* 1: run fwd+rev chains in the two halves of one warp (P<=16) */
+    int32_t pack_half_warps;          /* ignored since 0.2.0 (every run is a group of 8 lanes now); kept for layout compatibility */
     double target_accept;
     double init_step_size;
     double max_delta_energy;

@@ -170,31 +170,9 @@ constexpr int kNutsWarps = 4;
 constexpr int kMapWarps = 4;
 constexpr int kPpcWarps = 4;
 
-template <int MODEL, int NPL, int GW, bool SPARE>
-int launch_nuts_spare(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl) {
-    auto kern = nuts_kernel<MODEL, NPL, GW, kNutsWarps, SPARE>;
-    int grid = persistent_grid(kern, kNutsWarps * 32, 0, ctx->num_sms, fl.n_items, kNutsWarps);
-    kern<<<grid, kNutsWarps * 32, 0, st>>>(fl);
-    MDG_CUDA_TRY(cudaGetLastError());
-    ctx->timings.n_launches++;
-    return MDG_OK;
-}
-
-template <int MODEL, int NPL, int GW>
-int launch_nuts(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl) {
-    // does every run of this launch leave the last slot of its lane group free?
-    bool spare = true;
-    if (GW == 16) spare = fl.P < NPL * GW;  // halves run masks 1 and 2: P positions each
-    else for (int m = fl.mask0; m < fl.mask0 + fl.n_masks; ++m) spare = spare && ((m == 0 ? 2 * fl.P : fl.P) < NPL * GW);
-    return spare ? launch_nuts_spare<MODEL, NPL, GW, true>(ctx, st, fl) : launch_nuts_spare<MODEL, NPL, GW, false>(ctx, st, fl);
-}
-
-template <int MODEL>
-int launch_nuts_dispatch(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl, int npl, int gw) {
-    if (gw == 16) return launch_nuts<MODEL, 1, 16>(ctx, st, fl);
-    if (npl == 1) return launch_nuts<MODEL, 1, 32>(ctx, st, fl);
-    if (npl == 2) return launch_nuts<MODEL, 2, 32>(ctx, st, fl);
-    return launch_nuts<MODEL, 4, 32>(ctx, st, fl);
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 // K4, group layout: GW lanes per chain, rolled position loop (mdg_nuts_kernel.cuh)
@@ -206,7 +184,11 @@ int launch_nuts_group(mdg_ctx* ctx, cudaStream_t st, FitLaunch fl, DevBuf& acc) 
     fl.n_slots = (n_obs + 1 + GW - 1) / GW;  // index 0 is the spare
     const size_t smem = (size_t)kNutsWarps * nuts_warp_smem_bytes(fl.n_slots);
     MDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = persistent_grid(kern, kNutsWarps * 32, smem, ctx->num_sms, fl.n_items, kNutsWarps * (32 / GW));
+    // One group slot per item up to the whole GPU. (Smaller grids that leave every group several items were measured:
+    // 3 / 6 / 12 items per group cost 14 / 21 / 39 % at 10 000 TaxIDs per batch and 0 / 9 / 35 % at 40 000 — fewer
+    // resident chains, and different kernels sharing an SM's instruction cache; profiles/r02_nuts_tuning.md.)
+    const int per_group = std::max(1, env_int("MDG_ITEMS_PER_GROUP", 1));
+    const int grid = persistent_grid(kern, kNutsWarps * 32, smem, ctx->num_sms, fl.n_items, kNutsWarps * (32 / GW) * per_group);
     int rc = acc.ensure((size_t)grid * kNutsWarps * 4 * fl.n_slots * 32 * sizeof(double));
     if (rc) return rc;
     fl.waic_acc = acc.as<double>();
@@ -220,11 +202,6 @@ template <int MODEL>
 int launch_nuts_group_dispatch(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl, DevBuf& acc, int gw) {
     if (gw == 16) return launch_nuts_group<MODEL, 16>(ctx, st, fl, acc);
     return launch_nuts_group<MODEL, 8>(ctx, st, fl, acc);
-}
-
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
 }
 
 int launch_map(mdg_ctx* ctx, cudaStream_t st, const MapLaunch& ml, int npl) {
@@ -1005,7 +982,6 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
     const int P = max_position, R = 2 * P, S = cfg->num_samples, W = cfg->num_warmup;
     const bool host = (mem == MDG_HOST);
     const bool fwd_rev = cfg->do_fwd_rev != 0;
-    const bool pack = fwd_rev && cfg->pack_half_warps && P <= 16;
     const Priors pr = make_priors(*cfg);
 
     const int sample_runs = out_samples ? MDG_NUM_RUNS : (fwd_rev ? 3 : 1);
@@ -1136,25 +1112,12 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
             b.n_masks = 1; b.mask0 = 0; b.n_items = nc; b.work_counter = d_counters + 2;
             FitLaunch c = fl, d = fl;  // PMD / null, forward-only and reverse-only
             c.work_counter = d_counters + 3; d.work_counter = d_counters + 4;
-            const bool v1 = env_int("MDG_NUTS_V1", 0) != 0;  // round-1 kernel (one chain per warp / half warp), kept for A/B runs
-            if (v1 && pack) {
-                c.n_items = nc; d.n_items = nc; c.n_masks = 1; d.n_masks = 1; c.mask0 = 1; d.mask0 = 1;
-            } else {
-                c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_masks = 2; d.n_masks = 2; c.mask0 = 1; d.mask0 = 1;
-            }
-            if (v1) {
-                const int npl_half = pack ? 1 : npl_for(P, 32), gw_half = pack ? 16 : 32;
-                if (fwd_rev && (rc = launch_nuts_dispatch<0>(ctx, ln.side[1], c, npl_half, gw_half))) return bail(rc);
-                if ((rc = launch_nuts_dispatch<0>(ctx, ln.side[3], a, npl_for(R, 32), 32))) return bail(rc);
-                if (fwd_rev && (rc = launch_nuts_dispatch<1>(ctx, ln.side[2], d, npl_half, gw_half))) return bail(rc);
-                if ((rc = launch_nuts_dispatch<1>(ctx, ln.side[0], b, npl_for(R, 32), 32))) return bail(rc);
-            } else {
-                const int gw_all = env_int("MDG_GW_ALL", 8), gw_half = env_int("MDG_GW_HALF", 8);
-                if (fwd_rev && (rc = launch_nuts_group_dispatch<0>(ctx, ln.side[1], c, ln.waic_acc[2], gw_half))) return bail(rc);
-                if ((rc = launch_nuts_group_dispatch<0>(ctx, ln.side[3], a, ln.waic_acc[0], gw_all))) return bail(rc);
-                if (fwd_rev && (rc = launch_nuts_group_dispatch<1>(ctx, ln.side[2], d, ln.waic_acc[3], gw_half))) return bail(rc);
-                if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
-            }
+            c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_masks = 2; d.n_masks = 2; c.mask0 = 1; d.mask0 = 1;
+            const int gw_all = env_int("MDG_GW_ALL", 8), gw_half = env_int("MDG_GW_HALF", 8);  // lanes per chain (A/B runs: 16)
+            if (fwd_rev && (rc = launch_nuts_group_dispatch<0>(ctx, ln.side[1], c, ln.waic_acc[2], gw_half))) return bail(rc);
+            if ((rc = launch_nuts_group_dispatch<0>(ctx, ln.side[3], a, ln.waic_acc[0], gw_all))) return bail(rc);
+            if (fwd_rev && (rc = launch_nuts_group_dispatch<1>(ctx, ln.side[2], d, ln.waic_acc[3], gw_half))) return bail(rc);
+            if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
         }
         for (int i = 0; i < 4; ++i) {
             MDG_CUDA_TRY(cudaEventRecord(ln.join_ev[i], ln.side[i]));

@@ -188,6 +188,9 @@ __device__ __forceinline__ void eval_group(const double2* __restrict__ kn, doubl
     valid = fin && !any_bad;
 }
 
+#ifndef MDG_NUTS_MINBLOCKS
+#define MDG_NUTS_MINBLOCKS 4  // 128 registers per thread, 16 warps per SM (3 / 5 / 6 were measured slower: profiles/r01_nuts_tuning.md)
+#endif
 template <int MODEL, int GW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_kernel(const FitLaunch p) {
     constexpr int D = ModelDim<MODEL>::value;

@@ -307,8 +307,8 @@ def test_partition_and_order_invariance_bitwise(ctx):
     perm = np.random.default_rng(1).permutation(40)
     p = ctx.fit_batch(tid[perm], k[perm], N[perm], cfg)
     assert full["result"][perm].tobytes() == p["result"].tobytes()
-    unpacked = ctx.fit_batch(tid, k, N, cfg.copy(pack_half_warps=0))
-    assert full["result"].tobytes() == unpacked["result"].tobytes()  # half-warp packing changes nothing
+    again = ctx.fit_batch(tid, k, N, cfg)
+    assert full["result"].tobytes() == again["result"].tobytes()  # which group / warp / CTA picked a chain up changes nothing
     other = ctx.fit_batch(tid, k, N, cfg.copy(seed=7))
     assert other["result"]["q_mean"].tobytes() != full["result"]["q_mean"].tobytes()
     # the library's internal chunking (scratch reuse between chunks) changes nothing either
