@@ -92,6 +92,7 @@ struct mdg_ctx {
     cudaEvent_t epoch = nullptr;       // time zero of mdg_timings.nuts_begin_ms / nuts_end_ms
     cudaEvent_t inputs_ready = nullptr;
     mdg::DevBuf buf[mdg::kNumBufs];
+    mdg::DevBuf da_tables;             // sqrt(t) and t^-0.75 for t < kDaTable (dual averaging), filled at the first fit
     mdg_fit_lane lane[kFitLanes];
     mdg_fit_ticket_slot ticket[kFitTickets];
     int next_lane = 0;
@@ -342,6 +343,7 @@ void mdg_ctx_destroy(mdg_ctx* ctx) {
     }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->buf) b.release();
+    ctx->da_tables.release();
     for (int i = 0; i < kNumEvents; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->epoch) cudaEventDestroy(ctx->epoch);
     if (ctx->inputs_ready) cudaEventDestroy(ctx->inputs_ready);
@@ -1049,6 +1051,14 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
             if (!d_hi) d_hi = base + 2 * nt * R;
         }
     }
+    if (!ctx->da_tables.ptr) {
+        // the same libm calls as the reference arithmetic (t^-0.75 by pow, sqrt), made once on the host
+        std::vector<double> tab(2 * kDaTable);
+        for (int t = 0; t < kDaTable; ++t) { tab[t] = sqrt((double)t); tab[kDaTable + t] = t ? pow((double)t, -0.75) : 0.0; }
+        if ((rc = ctx->da_tables.ensure(tab.size() * sizeof(double)))) return bail(rc);
+        MDG_CUDA_TRY(cudaMemcpyAsync(ctx->da_tables.ptr, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        MDG_CUDA_TRY(cudaStreamSynchronize(st));  // `tab` is a stack-lifetime source
+    }
     if (d_trace) MDG_CUDA_TRY(cudaMemsetAsync(d_trace, 0xFF, nt * MDG_NUM_RUNS * (size_t)(W + S) * 4 * 8, st));
     if (out_samples) MDG_CUDA_TRY(cudaMemsetAsync(d_samples, 0xFF, nt * MDG_NUM_RUNS * (size_t)S * 4 * 8, st));
     // everything enqueued so far on the ctx stream (the caller's producers of the inputs, the copies above)
@@ -1097,6 +1107,7 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
         fl.n_tax = nc; fl.P = P; fl.cfg = *cfg; fl.pr = pr;
         fl.n_windows = adaptation_window_ends(W, fl.win_end);
         fl.rec = d_rec; fl.waic = d_waic; fl.samples = d_smp; fl.sample_runs = sample_runs;
+        fl.da_sqrt = ctx->da_tables.as<double>(); fl.da_pow = fl.da_sqrt + kDaTable;
         fl.trace = d_trace ? d_trace + (size_t)c0 * MDG_NUM_RUNS * (W + S) * 4 : nullptr;
         for (int r = 0; r < MDG_NUM_RUNS; ++r) fl.sample_slot[r] = out_samples ? r : ((r & 1) ? -1 : r / 2);
         MDG_CUDA_TRY(cudaEventRecord(ln.fork_ev, ls));

@@ -8,6 +8,7 @@ namespace mdg {
 
 constexpr int kMaxTreeDepth = 10;
 constexpr int kMaxWindows = 16;
+constexpr int kDaTable = 1024;  // entries of the dual-averaging tables sqrt(t), t^-0.75
 
 struct RunRecord {
     double step_size, mean_accept;
@@ -37,6 +38,8 @@ struct FitLaunch {
     int sample_runs;
     double* trace;      // [n_tax][6][W+S][4] or NULL
     int n_slots;        // rounds of the position loop, ceil((n_obs + 1) / GW)
+    const double* da_sqrt;  // [kDaTable] sqrt(t)
+    const double* da_pow;   // [kDaTable] t^-0.75 (dual averaging, hmc_util.dual_averaging kappa)
     double* waic_acc;   // WAIC accumulators, [grid * warps][4][n_slots][32]
 };
 

@@ -32,26 +32,22 @@
 namespace mdg {
 
 // momentum r ~ N(0, M), M^-1 = diag(imm): r_j = n_j * isd_j with isd = 1 / sqrt(imm) kept per chain (it changes at
-// the four adaptation-window ends only); Philox + Box-Muller out of line
+// the four adaptation-window ends only). The D standard normals are drawn ACROSS the lanes: lane j < D evaluates the
+// Philox block j / 2 and keeps component j % 2 of its Box-Muller pair (one Philox + one Box-Muller in the
+// instruction stream instead of two of each), then the values are broadcast.
 template <int D>
-__device__ MDG_COLD Vec4 draw_normals_cold(uint2 key, uint32_t c1, uint32_t c2, uint32_t c3) {
-    Vec4 r;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        double n0 = 0.0, n1 = 0.0;
-        if (2 * b < D) normal2(philox4x32(key, (uint32_t)b, c1, c2, c3), n0, n1);
-        r.v[2 * b] = n0;
-        r.v[2 * b + 1] = n1;
-    }
-    return r;
+__device__ MDG_COLD double draw_normal_lane_cold(uint2 key, uint32_t c1, uint32_t c2, uint32_t c3, int lig) {
+    double n0, n1;
+    normal2(philox4x32(key, (uint32_t)((lig >> 1) & ((D + 1) / 2 - 1)), c1, c2, c3), n0, n1);
+    return (lig & 1) ? n1 : n0;
 }
 
-template <int D>
+template <int D, int GW>
 __device__ __forceinline__ void draw_momentum_scaled(uint2 key, uint32_t c1, uint32_t c2, uint32_t c3, const double (&isd)[D],
-                                                     double (&r)[D]) {
-    const Vec4 n = draw_normals_cold<D>(key, c1, c2, c3);
+                                                     int lig, unsigned gmask, double (&r)[D]) {
+    const double mine = draw_normal_lane_cold<D>(key, c1, c2, c3, lig);
 #pragma unroll
-    for (int j = 0; j < D; ++j) r[j] = n.v[j] * isd[j];
+    for (int j = 0; j < D; ++j) r[j] = __shfl_sync(gmask, mine, j, GW) * isd[j];
 }
 
 enum GroupPhase : int { GP_FETCH = 0, GP_INIT = 1, GP_HEUR = 2, GP_LEAF = 3, GP_IDLE = 4 };
@@ -285,7 +281,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
     // begin a transition from the chain state held in sh.zp / sh.gp / pe_cur
     auto start_transition = [&]() {
         double r0[D];
-        draw_momentum_scaled<D>(key, (uint32_t)t, c2word(run_kind, P_MOM), 0u, sh.isd, r0);
+        draw_momentum_scaled<D, GW>(key, (uint32_t)t, c2word(run_kind, P_MOM), 0u, sh.isd, lig, gmask, r0);
         E0 = pe_cur + kinetic<D>(imm, r0);
         __syncwarp(gmask);
         if (lig == 0) {
@@ -311,7 +307,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
         bool large_ok = (h_step < 1.7976931348623157e308) || (h_dir <= 0);
         if (!(small_ok && large_ok && (h_last == 0 || h_dir == h_last))) return false;
         h_step *= (h_dir > 0 ? 2.0 : (h_dir < 0 ? 0.5 : 1.0));
-        draw_momentum_scaled<D>(key, h_call, c2word(run_kind, P_HEUR), h_att, sh.isd, rf);
+        draw_momentum_scaled<D, GW>(key, h_call, c2word(run_kind, P_HEUR), h_att, sh.isd, lig, gmask, rf);
         ++h_att;
         h_Er = kinetic<D>(imm, rf) + pe_cur;
         __syncwarp(gmask);
@@ -517,7 +513,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
                         start_doubling();
                     } else {
                         // ================= transition finished (hmc.py sample_kernel) =================
-                        const double accept_prob = m_sum_acc / (double)m_nprop;
+                        const double accept_prob = m_sum_acc * rcp_pos((double)m_nprop);
                         pe_cur = m_pe_p;
                         if (!m_is_c) roles.swap(LL_MAIN, LL_CUR);
                         __syncwarp(gmask);
@@ -528,9 +524,13 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
                         if (t < W) {
                             // ---- warmup_adapter.update_fn ----
                             da_t += 1;
-                            da_gavg = (1.0 - 1.0 / (da_t + 10)) * da_gavg + (p.cfg.target_accept - accept_prob) / (da_t + 10);
-                            da_x = da_prox - sqrt((double)da_t) / 0.05 * da_gavg;
-                            const double wt = exp_cold(-0.75 * log_cold((double)da_t));
+                            const double inv_t10 = rcp_pos((double)(da_t + 10));
+                            da_gavg = (1.0 - inv_t10) * da_gavg + (p.cfg.target_accept - accept_prob) * inv_t10;
+                            // sqrt(t) / gamma and t^-kappa (gamma = 0.05, kappa = 0.75) from the launch's tables (host libm)
+                            const bool tab = da_t < kDaTable;
+                            const double sq_t = tab ? __ldg(p.da_sqrt + da_t) : sqrt((double)da_t);
+                            da_x = da_prox - sq_t * 20.0 * da_gavg;
+                            const double wt = tab ? __ldg(p.da_pow + da_t) : exp_cold(-0.75 * log_cold((double)da_t));
                             da_xavg = (1.0 - wt) * da_xavg + wt * da_x;
                             eps = exp_cold((t == W - 1) ? da_xavg : da_x);
                             eps = fmax(eps, 2.2250738585072014e-308);
@@ -538,10 +538,11 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
                             if (is_middle) {
                                 wf_n += 1;
                                 if (lig == 0) {
+                                    const double inv_wf = rcp_pos((double)wf_n);
 #pragma unroll
                                     for (int j = 0; j < D; ++j) {
                                         double dpre = zc[j] - sh.wf_mean[j];
-                                        double mn = sh.wf_mean[j] + dpre / wf_n;
+                                        double mn = sh.wf_mean[j] + dpre * inv_wf;
                                         sh.wf_mean[j] = mn;
                                         sh.wf_m2[j] += dpre * (zc[j] - mn);
                                     }
@@ -573,16 +574,29 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
                         } else {
                             // ---- after warm-up: keep the draw ----
                             const int si = t - W;
-                            mean_accept += (accept_prob - mean_accept) / (double)(si + 1);
+                            const double inv_n = rcp_pos((double)(si + 1));
+                            mean_accept += (accept_prob - mean_accept) * inv_n;
                             if (m_div) ++n_div;
+                            // constrained draw (q, A, c, phi): lane j < D transforms parameter j, then a broadcast
                             double th[4];
-                            constrain<MODEL>(zc, p.pr.phi_min, th);
+                            {
+                                double myu = zc[0];
+#pragma unroll
+                                for (int j = 1; j < D; ++j) myu = (lig == j) ? zc[j] : myu;
+                                const double Ev = exp_fast(lig == D - 1 ? myu : -fabs(myu));
+                                const double iv = rcp_pos(1.0 + Ev);
+                                const double val = (lig == D - 1) ? Ev + p.pr.phi_min : (myu >= 0.0 ? iv : Ev * iv);
+                                th[0] = __shfl_sync(gmask, val, 0, GW);
+                                th[1] = MODEL == 0 ? __shfl_sync(gmask, val, 1, GW) : nan("");
+                                th[2] = MODEL == 0 ? __shfl_sync(gmask, val, 2, GW) : nan("");
+                                th[3] = __shfl_sync(gmask, val, D - 1, GW);
+                            }
                             if (lig == 0) {
                                 const double v[5] = {th[0], th[3], MODEL == 0 ? th[1] + th[2] : th[0], th[1], th[2]};
 #pragma unroll
                                 for (int j = 0; j < 5; ++j) {
                                     double dpre = v[j] - sh.acc_mean[j];
-                                    double mn = sh.acc_mean[j] + dpre / (double)(si + 1);
+                                    double mn = sh.acc_mean[j] + dpre * inv_n;
                                     sh.acc_mean[j] = mn;
                                     sh.acc_m2[j] += dpre * (v[j] - mn);
                                 }
@@ -595,13 +609,12 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
                             __syncwarp(gmask);
                             // WAIC: streaming logsumexp + Welford of this lane's log-likelihoods (fits.py:147-165)
                             const double* llc = llb + (size_t)roles.get(LL_CUR) * wstride + lane;
-                            const double inv_n = 1.0 / (double)(si + 1);
 #pragma unroll 1
                             for (int s = 0; s < NS; ++s) {
                                 const double v = llc[s * 32];
                                 double wmax = wacc[0 * wstride + s * 32], wsum = wacc[1 * wstride + s * 32];
                                 double wmean = wacc[2 * wstride + s * 32], wm2 = wacc[3 * wstride + s * 32];
-                                const double ed = exp_cold(-fabs(v - wmax));  // exp(-inf) = 0 on the first draw
+                                const double ed = exp_nonpos(-fabs(v - wmax));  // first draw: wmax = -inf, ed is ~1e-305 and multiplies wsum = 0
                                 if (v > wmax) { wsum = fma(wsum, ed, 1.0); wmax = v; }
                                 else wsum += ed;
                                 const double dpre = v - wmean;
