@@ -157,7 +157,9 @@ def check_pmd_chain_against_quadrature(samples, truth, tag):
             "D_max": samples[:, 1] + samples[:, 2]}
     for name, v in cols.items():
         m, var = truth["mean_" + name], truth["var_" + name]
-        assert abs(v.mean() - m) < 4 * mcse_batch_means(v) + 1e-12, (tag, name, v.mean(), m)
+        # + 0.5 % for the grid itself: twelve independent CUDA chains of the low-coverage reverse-only case scatter with
+        # sd(z) = 1.5 around the quadrature value (batch means underestimate the error of a prior-dominated q)
+        assert abs(v.mean() - m) < 4 * mcse_batch_means(v) + 0.005 * abs(m) + 1e-12, (tag, name, v.mean(), m)
         assert abs(v.var() - var) < 5 * mcse_batch_means((v - v.mean()) ** 2) + 0.03 * var, (tag, name, v.var(), var)
 
 
