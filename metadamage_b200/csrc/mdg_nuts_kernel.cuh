@@ -50,6 +50,55 @@ __device__ __forceinline__ void draw_momentum_scaled(uint2 key, uint32_t c1, uin
     for (int j = 0; j < D; ++j) r[j] = __shfl_sync(gmask, mine, j, GW) * isd[j];
 }
 
+// The five lgamma/digamma evaluations of one PMD position, x = {k + alpha, N - k + beta, N + phi, alpha, beta}
+// (mdg_common.cuh lgam_digam_batch), returning what the log-likelihood needs: d14 = lgamma(x0) - lgamma(x3),
+// d25 = lgamma(x1) - lgamma(x4), l3 = lgamma(x2) and the five digammas. The x < 10 shifts are organised by how
+// often they happen: alpha = D phi (and with it k + alpha at low counts) is below 10 for some lane of the warp on
+// most trips, the other three arguments almost never (phi < 10 or a handful of reads). So ONE branch covers the
+// pair (x0, x3) and takes a single logarithm for both, log(P(x3) / P(x0)) — the two -log P(x) corrections enter
+// d14 with opposite signs — and one more, rarely taken, covers the rest. (ncu, r2m capture: the five separate
+// per-argument blocks were 13 % of the executed instructions at 10-17 active lanes.)
+__device__ __forceinline__ void pmd_special(const double (&x)[5], double& d14, double& d25, double& l3, double (&dg)[5]) {
+    bool small[5];
+    double y[5], t[5], lg[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        small[i] = x[i] < 10.0;
+        y[i] = x[i] + (small[i] ? 10.0 : 0.0);
+        t[i] = rcp_pos(y[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) stirling(y[i], t[i], lg[i], dg[i]);
+    d14 = lg[0] - lg[3];
+    if (small[0] | small[3]) {
+        double P0, Q0, P3, Q3;
+        shift_poly10(x[0], P0, Q0);
+        shift_poly10(x[3], P3, Q3);
+        P0 = small[0] ? P0 : 1.0; Q0 = small[0] ? Q0 : 0.0;
+        P3 = small[3] ? P3 : 1.0; Q3 = small[3] ? Q3 : 0.0;
+        const double r0 = rcp_pos(P0), r3 = rcp_pos(P3);
+        // P3 <= P0 <= 3.4e11; the quotient leaves the normal range only for alpha < 1e-290 (|u_c| > 660)
+        d14 += (P3 > 1e-280) ? log_pos(P3 * r0) : (log_pos(P3) - log_pos(P0));
+        dg[0] = fma(-Q0, r0, dg[0]);
+        dg[3] = fma(-Q3, r3, dg[3]);
+    }
+    if (small[1] | small[2] | small[4]) {
+        const int idx[3] = {1, 2, 4};
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int i = idx[m];
+            if (small[i]) {
+                double P, Q;
+                shift_poly10(x[i], P, Q);
+                lg[i] -= log_pos(P);
+                dg[i] = fma(-Q, rcp_pos(P), dg[i]);
+            }
+        }
+    }
+    d25 = lg[1] - lg[4];
+    l3 = lg[2];
+}
+
 enum GroupPhase : int { GP_FETCH = 0, GP_INIT = 1, GP_HEUR = 2, GP_LEAF = 3, GP_IDLE = 4 };
 
 // bytes of dynamic shared memory per warp: {k, N} as doubles + four log-likelihood buffers, [n_slots][32] each
@@ -121,15 +170,15 @@ __device__ __forceinline__ void eval_group(const double2* __restrict__ kn, doubl
         double lls, ga, gb;
         if (MODEL == 0) {
             const double xs[5] = {d.x + al, d.y - d.x + be, d.y + phi, al, be};
-            double l5[5], d5[5];
-            lgam_digam_batch<5>(xs, gmask, l5, d5);
+            double d14, d25, l3v, d5[5];
+            pmd_special(xs, d14, d25, l3v, d5);
             if (s == 0) {  // the spare (index 0, k = N = 0) has just evaluated lgamma(phi), digamma(phi)
-                lgphi = __shfl_sync(gmask, l5[2], 0, GW);
+                lgphi = __shfl_sync(gmask, l3v, 0, GW);
                 dgphi = __shfl_sync(gmask, d5[2], 0, GW);
             }
-            // differences first: every term of an index with k = N = 0 is exactly zero, so the spare and
-            // the padding need no masking
-            lls = (l5[0] - l5[3]) + (l5[1] - l5[4]) - (l5[2] - lgphi);
+            // differences first: the terms of an index with k = N = 0 vanish (to 1e-16: the shared logarithm of
+            // d14 sees P(x3) / P(x0) = 1 up to rounding), so the spare and the padding need no masking
+            lls = d14 + d25 - (l3v - lgphi);
             const double dgN = d5[2] - dgphi;
             ga = (d5[0] - d5[3]) - dgN;
             gb = (d5[1] - d5[4]) - dgN;
