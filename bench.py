@@ -8,9 +8,11 @@
 
 A "step" is one pass of the hot path over one batch: counts_reduce (K1) over the synthetic mismatch
 matrix, then MAP + 6 NUTS runs + WAIC + posterior predictive + row assembly (K3-K7) for every TaxID that
-passes the cuts. Steps are pipelined the way the CLI's per-file loop is (mdg_fit_batch_submit / _wait, two
-batches in flight per GPU): the tail of a batch — a handful of long sequential chains — runs under the bulk
-of the next one. All K steps are inside the timed region and the last one is drained before the clock stops.
+passes the cuts. Steps go through the asynchronous C-ABI (mdg_fit_batch_submit / _wait); `--inflight 2` keeps two
+batches in flight per GPU so that the tail of a batch — a handful of long sequential chains — runs under the
+next one. The default is 1: with the straggler-free chains of numpyro's default adaptation the overlap costs 2-3 %
+(two different NUTS kernels sharing the SMs' instruction caches; profiles/r02_nuts_tuning.md) and buys nothing.
+All K steps are inside the timed region and the last one is drained before the clock stops.
 
 Workload: N = 1 -> BASELINE config 2 (10 000 fitted TaxIDs, seed 20240001, +-15 positions).
           N > 1 -> BASELINE config 3's generator (seed 20240002, min-alignments 10, min-y-sum 10), partitioned
@@ -80,7 +82,7 @@ def workload_config(args, world):
         "workload": what + f", +-{P} positions, counts + MAP + 6 NUTS runs (500 warm-up + 1000 draws) + WAIC + predictive D_max",
         "taxa_per_gpu": args.taxa_per_gpu, "max_position": P,
         "partition": f"by TaxID over {world} GPU(s), no collective on the fit path",
-        "pipelining": "two batches in flight per GPU (mdg_fit_batch_submit / _wait); every step is drained inside the timed region",
+        "pipelining": f"{args.inflight} batch(es) in flight per GPU (mdg_fit_batch_submit / _wait); every step is drained inside the timed region",
         "l2": "flushed between steps (256 MiB write); the counts inputs (>= 133 MB) exceed L2 as well"}
 
 
@@ -279,7 +281,7 @@ def counts_stress(ctx, torch, dev, n_rows=10_000_000, reps=5):
 class DeviceBatch:
     """Device-resident inputs of one workload plus two sets of output buffers (two steps are in flight)."""
 
-    def __init__(self, torch, dev, g, R):
+    def __init__(self, torch, dev, g, R, n_sets=2):
         from metadamage_b200._abi import FIT_RESULT_DTYPE
 
         n_rows, n_in_tax = len(g["tax_id"]), len(g["tax_ids"])
@@ -289,7 +291,7 @@ class DeviceBatch:
             is_reverse=torch.from_numpy(g["is_reverse"]).to(dev), pos0=torch.from_numpy(g["pos0"]).to(dev),
             counts16=torch.from_numpy(g["counts16"].view(np.int32)).to(dev))
         self.sets = []
-        for _ in range(2):
+        for _ in range(n_sets):
             outs = dict(
                 n_fwd_ref=torch.empty(n_rows, dtype=torch.int32, device=dev), n_rev_ref=torch.empty(n_rows, dtype=torch.int32, device=dev),
                 f_fwd=torch.empty(n_rows, dtype=torch.float32, device=dev), f_rev=torch.empty(n_rows, dtype=torch.float32, device=dev),
@@ -316,6 +318,7 @@ def main():
     ap.add_argument("--no-counts-stress", action="store_true")
     ap.add_argument("--no-seam", action="store_true")
     ap.add_argument("--no-full-pass", action="store_true", help="skip the 1M-TaxID single pass at N = 8")
+    ap.add_argument("--inflight", type=int, default=1, choices=[1, 2], help="batches in flight per GPU (MDG_MAX_INFLIGHT = 2)")
     ap.add_argument("--heuristic", type=int, default=0, help="find_heuristic_step_size (0 = numpyro 0.4.1 default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -351,7 +354,7 @@ def main():
     R = 2 * P
 
     g = workload(args, rank, world)
-    batch = DeviceBatch(torch, dev, g, R)
+    batch = DeviceBatch(torch, dev, g, R, args.inflight)
     n_rows, n_in_tax = batch.n_rows, batch.n_in_tax
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -377,19 +380,19 @@ def main():
 
     def run_pipelined(steps, submit, record=True):
         """`submit(i)` enqueues step i and returns (n_fit, ticket, counts timings); at most two steps in flight."""
-        pending, n = None, 0
+        pending, n, last = [], 0, None
         for i in range(steps):
+            if len(pending) == args.inflight:
+                last = ctx.fit_wait(pending.pop(0))
+                book(None, last["timings"], record)
             n_fit, ticket, t_counts = submit(i)
             book(t_counts, None, record)
             n += n_fit
-            if pending is not None:
-                book(None, ctx.fit_wait(pending)["timings"], record)
-            pending = ticket
-        if pending is not None:
-            last = ctx.fit_wait(pending)
+            pending.append(ticket)
+        while pending:
+            last = ctx.fit_wait(pending.pop(0))
             book(None, last["timings"], record)
-            return n, last
-        return n, None
+        return n, last
 
     def timed(steps, submit, record=True):
         barrier()
@@ -407,7 +410,7 @@ def main():
 
     def make_submit_device(b, fit_cfg):
         def submit(i):
-            s = b.sets[i % 2]
+            s = b.sets[i % len(b.sets)]
             flush.zero_()  # evict L2 between steps
             n_fit = ctx.counts_reduce_device(b.cols, s["outs"])
             t1 = ctx.timings()
@@ -440,7 +443,7 @@ def main():
     h = {key: pinned(g[key]) for key in ("tax_id", "n_alignments", "is_reverse", "pos0", "counts16")}
     e2e_bytes = {"h2d": 0, "d2h": 0}
     host_sets = []
-    for _ in range(2):
+    for _ in range(args.inflight):
         host_sets.append(dict(
             counts=dict(
                 n_fwd_ref=pinned_empty(n_rows, np.uint32), n_rev_ref=pinned_empty(n_rows, np.uint32), f_fwd=pinned_empty(n_rows, np.float32),
@@ -452,7 +455,7 @@ def main():
                      hpdi_lo=pinned_empty((n_in_tax, R), np.float32), hpdi_hi=pinned_empty((n_in_tax, R), np.float32))))
 
     def submit_host(i):
-        s = host_sets[i % 2]
+        s = host_sets[i % len(host_sets)]
         flush.zero_()
         r = ctx.counts_reduce(h["tax_id"], h["n_alignments"], h["is_reverse"], h["pos0"], h["counts16"],
                               max_position=P, want_noise=True, out=s["counts"])
@@ -482,7 +485,7 @@ def main():
         torch.cuda.empty_cache()
         n_full = 1_000_000 // world
         gf = workload(args, rank, world, n_fit=n_full)
-        bf = DeviceBatch(torch, dev, gf, R)
+        bf = DeviceBatch(torch, dev, gf, R, 1)
         submit_full = make_submit_device(bf, cfg)
         run_pipelined(1, submit_full, record=False)
         fs = ClockSampler(local_rank).start()
@@ -510,7 +513,7 @@ def main():
     chain_stats = {"mean_leapfrogs_per_chain": float(chain_sum[0].item() / chain_sum[1].item()),
                    "max_leapfrogs_of_one_chain": float(chain_max.item()),
                    "failed_fits_rank0": int((status & 1).sum()),
-                   "note": "a chain is sequential; the tail of a batch (its longest chains) runs under the next batch"}
+                   "note": "a chain is sequential: a batch ends with its longest chains (--inflight 2 runs them under the next batch)"}
 
     # ---------------- rooflines, seam, CPU baseline (rank 0 only) ----------------
     if rank == 0:
@@ -561,7 +564,7 @@ def main():
             "reduced_unit": {"value": red_fits / (red_ms * 1e-3), "unit": UNIT, "ms_per_step": red_ms, "steps": 1,
                              "what": "counts + MAP + PMD/null NUTS on all positions + WAIC + predictive D_max, WITHOUT the forward-only / "
                                      "reverse-only refits of fits.py:298-356 (the north star's reduced unit; `value` above is the full fit); "
-                                     "one unpipelined step"},
+                                     "one step"},
             "cfg3_full_pass": full_pass,
             "cpu_baseline": cpu,
             "kernel_ms_per_step": {"counts": per_step("counts_ms"), "map": per_step("map_ms"), "nuts": per_step("nuts_ms"),
@@ -602,8 +605,8 @@ def seam_timing(g, args, abi_e2e_ms):
     out["unit"] = UNIT
     out["overhead_vs_abi_e2e"] = out["total_s"] / (abi_e2e_ms * 1e-3) - 1.0
     out["what"] = ("wall clock of counts.compute_counts_with_dask(cfg) + fits.compute_fits(df_counts, cfg, mcmc_kwargs) on the cfg2 workload "
-                   "written as a 22-column TSV (file read, GPU tokeniser, K1, DataFrames, K3-K7, result DataFrames included; one "
-                   "unpipelined batch), second of two runs; overhead is relative to one pipelined C-ABI e2e step")
+                   "written as a 22-column TSV (file read, GPU tokeniser, K1, DataFrames, K3-K7, result DataFrames included), "
+                   "second of two runs; overhead is relative to one C-ABI e2e step")
     return out
 
 

@@ -74,7 +74,9 @@ enum mdg_run_kind {
                                       * the bounded-work analogue of the reference's per-fit timeout
                                       * (fits.py:37-38, 472-474); always set together with MDG_FIT_FAILED */
 
+#ifndef MDG_MAX_INFLIGHT
 #define MDG_MAX_INFLIGHT 2         /* batches one ctx keeps in flight between mdg_fit_batch_submit and _wait */
+#endif
 #define MDG_MAX_POSITION 64        /* max_position supported by the fit kernels */
 #define MDG_MAX_SEGMENT_ROWS 2048  /* rows of one TaxID the counts kernel can hold in one tile */
 

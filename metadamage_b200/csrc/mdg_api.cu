@@ -80,8 +80,8 @@ struct mdg_fit_ticket_slot {
     bool have_nuts = false;
 };
 
-constexpr int kFitLanes = 2;
-constexpr int kFitTickets = 2;
+constexpr int kFitLanes = MDG_MAX_INFLIGHT;
+constexpr int kFitTickets = MDG_MAX_INFLIGHT;
 
 struct mdg_ctx {
     int device = 0;
@@ -1110,6 +1110,14 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
         fl.da_sqrt = ctx->da_tables.as<double>(); fl.da_pow = fl.da_sqrt + kDaTable;
         fl.trace = d_trace ? d_trace + (size_t)c0 * MDG_NUM_RUNS * (W + S) * 4 : nullptr;
         for (int r = 0; r < MDG_NUM_RUNS; ++r) fl.sample_slot[r] = out_samples ? r : ((r & 1) ? -1 : r / 2);
+        // Overlap with the chunk in flight on another lane is wanted for its TAIL only (a few long chains on an
+        // otherwise idle GPU), not for its bulk: two different NUTS kernels sharing the SMs evict each other from
+        // the instruction cache (measured: -2..-5 % with unrestricted overlap). So this chunk's NUTS launches wait
+        // until the other chunk's first three launches are through and only its last one (null model, all
+        // positions: short, uniform chains) is still running.
+        for (auto& other : ctx->lane)
+            if (&other != &ln && other.busy)
+                for (int i = 1; i < 4; ++i) MDG_CUDA_TRY(cudaStreamWaitEvent(ls, other.join_ev[i], 0));
         MDG_CUDA_TRY(cudaEventRecord(ln.fork_ev, ls));
         for (int i = 0; i < 4; ++i) MDG_CUDA_TRY(cudaStreamWaitEvent(ln.side[i], ln.fork_ev, 0));
         {

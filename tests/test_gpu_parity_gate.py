@@ -97,3 +97,46 @@ def test_cfg4_parity_gate_64_taxa(ctx, oracle):
     tid, k, N = pick_taxa(640, 16, 48, 25, syn.SEEDS["cfg4"], fwd="GA", rev="CT")
     got, _ = run_gate(ctx, oracle, tid, k, N, 0, "cfg4 P=25 GA/CT")
     assert np.median(got["result"]["n_sigma"]) < 2.0   # the control run sees no damage
+
+
+def test_cfg2_parity_gate_independent_streams(ctx, oracle):
+    """The same gate with the two sides on DIFFERENT Philox seeds: the chains share nothing but the posterior,
+    so the z-scores must look like unit-variance noise (sd close to 1, a little above because batch means
+    underestimate the error of the stickier low-coverage chains)."""
+    tid, k, N = pick_taxa(2560, 64, 192, 15, syn.SEEDS["cfg2"])
+    got = ctx.fit_batch(tid, k, N, _lib.default_config(seed=20260001), want_samples=True)
+    exp = oracle.fit_batch(tid, k, N, oracle.default_config(seed=0), want_samples=True)
+    zs = {}
+    for i in range(len(tid)):
+        for name, z in z_scores(got["samples"][i, 0], exp["samples"][i, 0]).items():
+            zs.setdefault(name, []).append(z)
+    allz = np.concatenate([np.asarray(v) for v in zs.values()])
+    summary = {name: (float(np.mean(v)), float(np.mean(np.abs(v) > 3.0)), float(np.std(v))) for name, v in zs.items()}
+    msg = f"independent streams: (mean z, share beyond 3, sd z) = {summary}; pooled share beyond 3 = {np.mean(np.abs(allz) > 3):.4f}"
+    print(msg)
+    assert np.mean(np.abs(allz) > 3.0) <= 0.02, msg
+    for name, (mz, share, sd) in summary.items():
+        assert abs(mz) < 0.2 and 0.8 < sd < 1.5 and share <= 0.03, msg
+
+
+def test_round1_straggler_taxid_chain_lengths(ctx):
+    """Round 1's weak-scaling bench was capped at 0.585 by ONE chain: rank 1's shard (generator seed cfg2 + 1000),
+    fitted TaxID 4305, PMD / reverse-only, ran 464 068 leapfrogs at a collapsed step size of 0.0058 (mean chain:
+    9.8 k) under find_heuristic_step_size = 1. The chain is re-fitted here under both settings of the switch; its
+    length is reported, bounded for the shipped default, and a leapfrog budget turns a runaway chain into a
+    flagged, dropped fit (the reference's timeout, fits.py:472-474) instead of a straggler."""
+    from metadamage_b200._abi import FIT_BUDGET_EXCEEDED, FIT_FAILED
+
+    tid, k, N, _ = syn.dense_fit_batch(10_000, seed=syn.SEEDS["cfg2"] + 1000, tax_id_start=1 + 100_000_000)
+    sel = slice(4305, 4306)
+    report = {}
+    for heuristic in (0, 1):
+        r = ctx.fit_batch(tid[sel], k[sel], N[sel], _lib.default_config(find_heuristic_step_size=heuristic))["result"][0]
+        report[heuristic] = dict(leapfrogs=r["run"]["n_leapfrog"].tolist(), step_size_pmd_rev=float(r["run"][4]["step_size"]), status=int(r["status"]))
+        assert (r["status"] & FIT_FAILED) == 0
+    print("round-1 straggler TaxID:", report)
+    assert max(report[0]["leapfrogs"]) < 200_000, report
+    longest = max(report[1]["leapfrogs"])
+    capped = ctx.fit_batch(tid[sel], k[sel], N[sel], _lib.default_config(find_heuristic_step_size=1, max_leapfrogs_per_run=longest // 2))["result"][0]
+    assert capped["status"] & FIT_BUDGET_EXCEEDED and capped["status"] & FIT_FAILED
+    assert capped["run"]["n_leapfrog"].max() <= longest // 2 + 1
