@@ -220,8 +220,12 @@ def _assemble_df_counts(pieces, cfg):
     270-272). Pieces are internally ordered already; a k-way merge by (N_alignments, tax_id) descending joins them."""
     fwd, rev = cfg.substitution_bases_forward, cfg.substitution_bases_reverse
     P = int(cfg.max_position)
-    rows = {key: np.concatenate([p["rows"][key] for p in pieces], axis=1 if key == "counts16" else 0) for key in pieces[0]["rows"]}
-    tax = {key: np.concatenate([p["tax"][key][p["tax_order"]] for p in pieces]) for key in pieces[0]["tax"] if key != "first_row"}
+    if len(pieces) == 1:
+        rows = pieces[0]["rows"]
+        tax = {key: val[pieces[0]["tax_order"]] for key, val in pieces[0]["tax"].items() if key != "first_row"}
+    else:
+        rows = {key: np.concatenate([p["rows"][key] for p in pieces], axis=1 if key == "counts16" else 0) for key in pieces[0]["rows"]}
+        tax = {key: np.concatenate([p["tax"][key][p["tax_order"]] for p in pieces]) for key in pieces[0]["tax"] if key != "first_row"}
     # rows per kept TaxID, in each piece's output order
     seg_len = np.concatenate([np.diff(np.r_[np.flatnonzero(np.r_[True, p["rows"]["tax_id"][1:] != p["rows"]["tax_id"][:-1]]),
                                             len(p["rows"]["tax_id"])]) if len(p["rows"]["tax_id"]) else np.zeros(0, np.int64)
@@ -239,9 +243,17 @@ def _assemble_df_counts(pieces, cfg):
         ranks = [ranks[t] for t in order]
     n_tax = len(seg_len)
     group_of_row = np.repeat(np.arange(n_tax), seg_len)
-    data = {"tax_id": rows["tax_id"], "tax_name": _categorical_from_groups(names, group_of_row) if n_tax else [],
+    n_rows = len(group_of_row)
+    # categorical columns straight from integer codes (what astype("category") would build, without hashing
+    # every row): tax_id and the strings are per-TaxID values, the strand has two
+    uniq_tax, inv_tax = np.unique(tax["tax_id"], return_inverse=True)
+    strand_present = np.unique(rows["is_reverse"] != 0)
+    strand_cats = np.array(["3'", "5'"], dtype=object)[[0] if strand_present.tolist() == [True] else ([1] if strand_present.tolist() == [False] else [0, 1])]
+    strand_codes = np.zeros(n_rows, np.int8) if len(strand_cats) == 1 else np.where(rows["is_reverse"] != 0, 0, 1).astype(np.int8)
+    data = {"tax_id": pd.Categorical.from_codes(inv_tax[group_of_row], categories=uniq_tax) if n_tax else rows["tax_id"],
+            "tax_name": _categorical_from_groups(names, group_of_row) if n_tax else [],
             "tax_rank": _categorical_from_groups(ranks, group_of_row) if n_tax else [], "N_alignments": rows["n_alignments"],
-            "strand": np.where(rows["is_reverse"] == 1, "3'", "5'"), "position": rows["z"]}
+            "strand": pd.Categorical.from_codes(strand_codes, categories=strand_cats) if n_rows else [], "position": rows["z"]}
     for i, name in enumerate(REF_OBS_BASES):
         data[name] = rows["counts16"][i]
     # the reference's column layout (counts.py:88, 111, 201-203): a reference-base column shared by both
@@ -250,10 +262,11 @@ def _assemble_df_counts(pieces, cfg):
     data[rev[0]] = rows["n_rev_ref"]
     data[f"f_{fwd}"] = rows["f_fwd"]
     data[f"f_{rev}"] = rows["f_rev"]
-    data["y_sum_total"] = rows["y_sum_total"]
-    df = pd.DataFrame(data)
-    df["shortname"] = cfg.shortname
-    df = utils.downcast_dataframe(df, ["tax_id", "tax_name", "tax_rank", "strand", "shortname"])
+    if n_rows and rows["y_sum_total"].max() > np.iinfo(np.uint32).max:
+        raise AssertionError("Dataframe contains too large values.")  # utils.py:338-339
+    data["y_sum_total"] = rows["y_sum_total"].astype(np.uint32)
+    data["shortname"] = pd.Categorical.from_codes(np.zeros(n_rows, np.int8), categories=[cfg.shortname])
+    df = pd.DataFrame(data)  # every column already has its final dtype (utils.downcast_dataframe would change nothing)
     # K1's dense per-TaxID outputs are remembered for this very DataFrame object (df_counts order), so that
     # compute_fits does not rebuild them from the rows
     first_row = np.r_[0, np.cumsum(seg_len)[:-1]].astype(np.int64) if n_tax else np.zeros(0, np.int64)
