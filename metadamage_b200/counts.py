@@ -65,6 +65,8 @@ def soa_columns(df):
     """DataFrame -> the SoA arrays of the C-ABI."""
     if len(df) and (df[REF_OBS_BASES].to_numpy().max() > np.iinfo(np.uint32).max or df["N_alignments"].max() > np.iinfo(np.uint32).max):
         raise AssertionError("Dataframe contains too large values.")
+    if len(df) and not (0 <= df["position"].min() and df["position"].max() <= 254):
+        raise ValueError("position must be in [0, 254] (the GPU tokeniser enforces the same range)")
     return dict(
         tax_id=df["tax_id"].to_numpy(np.int64),
         n_alignments=df["N_alignments"].to_numpy(np.uint32),

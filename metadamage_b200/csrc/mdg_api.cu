@@ -696,6 +696,17 @@ int mdg_tsv_parse(mdg_ctx* ctx, int mem, const char* text, int64_t n_bytes, int6
     *out_n_rows = 0;
     if (out_n_cols) *out_n_cols = 0;
     ctx->timings = mdg_timings{};
+    if (n_bytes > 0) {
+        // `text` is read on the host (header / layout detection): a device pointer is an error, not a crash
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+            set_error("mdg_tsv_parse: text must be a host pointer (mem only says where the OUTPUT columns live)");
+            return MDG_ERR_INVALID;
+        }
+        (void)cudaGetLastError();
+    }
+    // blank lines at the end of the file are not rows (pandas.read_csv skips them too)
+    while (n_bytes > 0 && (text[n_bytes - 1] == '\n' || text[n_bytes - 1] == '\r')) --n_bytes;
     // header detection and layout from the first line (host)
     int64_t first = 0;
     {

@@ -108,6 +108,26 @@ def test_gpu_tsv_edge_cases(ctx):
         ctx.tsv_parse(one.replace(b"\t12\t", b"\t99999999999\t") + b"\n")
     with pytest.raises(MdgError, match="columns"):
         ctx.tsv_parse(b"1\t2\t3\n")
+    # blank lines at the end of the file are not rows (pandas.read_csv skips them)
+    r = ctx.tsv_parse(one + b"\n" + one + b"\n\n\r\n")
+    assert r["n_rows"] == 2 and r["tax_id"].tolist() == [7, 7]
+    assert ctx.tsv_parse(b"\n\n")["n_rows"] == 0
+    # the text is a host pointer whatever `mem` says; a device pointer is refused, not dereferenced
+    import ctypes as C
+
+    import torch
+
+    from metadamage_b200._abi import MDG_DEVICE
+
+    dev_text = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    cap = 4
+    cols = [torch.empty(cap, dtype=torch.int64, device="cuda"), torch.empty(cap, dtype=torch.int32, device="cuda"),
+            torch.empty(cap, dtype=torch.uint8, device="cuda"), torch.empty(cap, dtype=torch.uint8, device="cuda"),
+            torch.empty((16, cap), dtype=torch.int32, device="cuda")]
+    n_rows, n_cols = C.c_int64(0), C.c_int32(0)
+    rc = ctx._lib.mdg_tsv_parse(ctx._h, MDG_DEVICE, C.cast(dev_text.data_ptr(), C.c_char_p), 64, cap, *[C.c_void_p(t.data_ptr()) for t in cols], cap,
+                                None, None, C.byref(n_rows), C.byref(n_cols))
+    assert rc == -1 and b"host pointer" in ctx._lib.mdg_last_error()
 
 
 @pytest.mark.gpu
