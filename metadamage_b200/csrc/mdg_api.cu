@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "mdg_counts_kernel.cuh"
+#include "mdg_counts_stream.cuh"
 #include "mdg_tsv_kernel.cuh"
 #include "mdg_select_kernel.cuh"
 #include "mdg_post_kernels.cuh"
@@ -498,12 +499,9 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
     cl.use_tma = aligned16(cl.tax_id) && aligned16(cl.n_align) && aligned16(cl.is_rev) && aligned16(cl.pos0) &&
                  aligned16(cl.counts16) && (cl.stride % 4 == 0);
 
-    // ---- tiling ladder: widen the lookahead if a TaxID does not fit ----
     // output bases 16-byte aligned -> 128-bit stores
     cl.vec_out = aligned16(cl.n_fwd_row) && aligned16(cl.n_rev_row) && aligned16(cl.f_fwd_row) && aligned16(cl.f_rev_row) &&
                  aligned16(cl.z_row) && aligned16(cl.y_row) && aligned16(cl.keep_row);
-    static const int ladder_T[3] = {448, 512, 512};
-    static const int ladder_L[3] = {64, 512, MDG_MAX_SEGMENT_ROWS};
     int rc = ctx->buf[2].ensure(64);
     if (rc) return rc;
     long long* d_ntax = ctx->buf[2].as<long long>();
@@ -511,6 +509,73 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
     unsigned int* d_ticket = reinterpret_cast<unsigned int*>(d_ntax + 2);
     int h_err = 0;
     long long h_ntax = 0;
+    const bool stream_design = getenv("MDG_COUNTS_TILES") == nullptr;  // the round-1 tile kernel stays selectable for A/B runs
+    if (stream_design) {
+        // ---- warp-synchronous streaming kernel (mdg_counts_stream.cuh): one warp per 128 rows ----
+        const long long n_tiles = (n_rows + kStreamRows - 1) / kStreamRows;
+        const size_t ncap_t = (size_t)out_capacity;
+        const long long n_chunks_cap = (n_tiles + kScanChunk - 1) / kScanChunk;
+        rc = ctx->buf[3].ensure((size_t)n_tiles * (8 + 8 + 4) + (size_t)n_chunks_cap * 8 + 64);
+        if (rc) return rc;
+        long long* d_tile_base = ctx->buf[3].as<long long>();
+        long long* d_final_base = d_tile_base + n_tiles;
+        long long* d_chunk = d_final_base + n_tiles;
+        int* d_tile_cnt = reinterpret_cast<int*>(d_chunk + n_chunks_cap);
+        const size_t tmp_bytes = ncap_t * (8 + 4 + 8 + 8 + (size_t)R * 8) + 256 * 8;
+        rc = ctx->buf[21].ensure(tmp_bytes);
+        if (rc) return rc;
+        unsigned char* tb = ctx->buf[21].as<unsigned char>();
+        size_t to = 0;
+        auto tmp = [&](size_t bytes) { void* q = tb + to; to += (bytes + 255) & ~(size_t)255; return q; };
+        // the noise kernel needs the first rows in final order even if the caller does not want them
+        long long* d_first_final = cl.out_first ? cl.out_first : (cl.out_noise ? (long long*)tmp(ncap_t * 8) : nullptr);
+        CountsPermute cp = {};
+        cp.n_tiles = n_tiles; cp.tile_base = d_tile_base; cp.final_base = d_final_base; cp.tile_cnt = d_tile_cnt; cp.R = R;
+        cp.chunk_off = d_chunk;
+        cp.out_tax = cl.out_tax; cp.out_nal = cl.out_nal; cp.out_first = d_first_final; cp.out_k = cl.out_k; cp.out_N = cl.out_N;
+        cp.out_noise = nullptr;
+        CountsLaunch kl = cl;  // the tile kernel writes the per-TaxID rows into the temporaries
+        kl.out_noise = nullptr;
+        kl.out_first = nullptr;
+        if (cl.out_tax) { cp.t_tax = (long long*)tmp(ncap_t * 8); kl.out_tax = (long long*)cp.t_tax; }
+        if (cl.out_nal) { cp.t_nal = (uint32_t*)tmp(ncap_t * 4); kl.out_nal = (uint32_t*)cp.t_nal; }
+        if (d_first_final) { cp.t_first = (long long*)tmp(ncap_t * 8); kl.out_first = (long long*)cp.t_first; }
+        if (cl.out_k) { cp.t_k = (uint32_t*)tmp(ncap_t * R * 4); kl.out_k = (uint32_t*)cp.t_k; }
+        if (cl.out_N) { cp.t_N = (uint32_t*)tmp(ncap_t * R * 4); kl.out_N = (uint32_t*)cp.t_N; }
+        kl.tile_ticket = d_ticket;
+        kl.kept_counter = reinterpret_cast<unsigned long long*>(d_ntax + 3);
+        kl.tile_base = d_tile_base;
+        kl.tile_cnt = d_tile_cnt;
+        kl.capacity = out_capacity;
+        kl.error_flag = d_err;
+        MDG_CUDA_TRY(cudaMemsetAsync(d_ntax, 0, 64, st));
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+        counts_stream_kernel<<<(unsigned)((n_tiles + kStreamWarps - 1) / kStreamWarps), kStreamWarps * 32, 0, st>>>(kl);
+        MDG_CUDA_TRY(cudaGetLastError());
+        const long long n_chunks = (n_tiles + kScanChunk - 1) / kScanChunk;
+        counts_scan_local_kernel<<<(unsigned)n_chunks, kScanChunk, 0, st>>>(d_tile_cnt, n_tiles, d_final_base, d_chunk);
+        counts_scan_chunks_kernel<<<1, 32, 0, st>>>(d_chunk, n_chunks, d_ntax);
+        MDG_CUDA_TRY(cudaGetLastError());
+        ctx->timings.n_launches += 1;
+        counts_permute_kernel<<<(unsigned)((n_tiles + kPermuteWarps - 1) / kPermuteWarps), kPermuteWarps * 32, 0, st>>>(cp);
+        MDG_CUDA_TRY(cudaGetLastError());
+        ctx->timings.n_launches += 3;
+        if (cl.out_noise) {
+            NoiseLaunch nl = {};
+            nl.n_rows = n_rows; nl.tax_id = cl.tax_id; nl.is_rev = cl.is_rev; nl.pos0 = cl.pos0; nl.counts16 = cl.counts16;
+            nl.stride = cl.stride; nl.P = P; nl.n_tax = d_ntax; nl.first_row = d_first_final; nl.out_noise = cl.out_noise;
+            nl.capacity = out_capacity;
+            counts_noise_kernel<<<(unsigned)std::max<long long>(1, std::min<long long>((out_capacity + 3) / 4, 16LL * ctx->num_sms)), 128, 0, st>>>(nl);
+            MDG_CUDA_TRY(cudaGetLastError());
+            ctx->timings.n_launches += 1;
+        }
+        MDG_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+        MDG_CUDA_TRY(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MDG_CUDA_TRY(cudaMemcpyAsync(&h_ntax, d_ntax, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        MDG_CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+    static const int ladder_T[3] = {448, 512, 512};
+    static const int ladder_L[3] = {64, 512, MDG_MAX_SEGMENT_ROWS};
     const size_t row_bytes = (size_t)kCountsBytesPerRow + 4 * (size_t)cl.ncols;
     const size_t fixed_bytes = 16 + 16 + (size_t)kCountsWarps * 2 * R * 4 + 256;
     for (int step = 0; step < 3; ++step) {
@@ -564,7 +629,7 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
         MDG_CUDA_TRY(cudaGetLastError());
         counts_scan_kernel<<<1, 1024, 0, st>>>(d_tile_cnt, n_tiles, d_final_base, d_ntax);
         MDG_CUDA_TRY(cudaGetLastError());
-        counts_permute_kernel<<<(unsigned)std::min<long long>(n_tiles, 4LL * ctx->num_sms * 4), 128, 0, st>>>(cp);
+        counts_permute_kernel<<<(unsigned)((n_tiles + kPermuteWarps - 1) / kPermuteWarps), kPermuteWarps * 32, 0, st>>>(cp);
         MDG_CUDA_TRY(cudaGetLastError());
         MDG_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
         ctx->timings.n_launches += 3;
@@ -572,6 +637,7 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
         MDG_CUDA_TRY(cudaMemcpyAsync(&h_ntax, d_ntax, sizeof(long long), cudaMemcpyDeviceToHost, st));
         MDG_CUDA_TRY(cudaStreamSynchronize(st));
         if (h_err != CE_SEGMENT_TOO_LONG) break;
+    }
     }
     if (h_err == CE_SEGMENT_TOO_LONG) {
         set_error("mdg_counts_reduce: a TaxID has more than %d rows (rows must be grouped by tax_id)", MDG_MAX_SEGMENT_ROWS);

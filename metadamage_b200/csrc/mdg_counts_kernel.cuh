@@ -491,23 +491,80 @@ __global__ void __launch_bounds__(kCountsThreads, MDG_COUNTS_MINBLOCKS) counts_r
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) counts_scan_kernel(const int* __restrict__ tile_cnt, long long n_tiles,
                                                            long long* __restrict__ final_base, long long* __restrict__ n_tax_out) {
-    __shared__ long long s_part[1024];
-    const int tid = threadIdx.x;
-    const long long per = (n_tiles + 1023) / 1024;
-    const long long lo = (long long)tid * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
-    long long sum = 0;
-    for (long long t = lo; t < hi; ++t) sum += tile_cnt[t];
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const long long v = tid >= o ? s_part[tid - o] : 0;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
+    // warp w scans a contiguous range with coalesced 32-element steps and a running carry; the 32 warp totals are
+    // scanned by warp 0; a second coalesced pass adds each warp's offset
+    __shared__ long long s_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long per = ((n_tiles + 31) / 32 + 31) / 32 * 32;  // elements per warp, a multiple of 32
+    const long long lo = (long long)warp * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    long long running = 0;
+    for (long long i = lo; i < hi; i += 32) {
+        const long long t = i + lane;
+        const long long v = t < hi ? (long long)tile_cnt[t] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (t < hi) final_base[t] = running + incl - v;
+        running += __shfl_sync(0xffffffffu, incl, 31);
     }
-    long long run = s_part[tid] - sum;
-    for (long long t = lo; t < hi; ++t) { final_base[t] = run; run += tile_cnt[t]; }
-    if (tid == 1023) *n_tax_out = s_part[1023];
+    if (lane == 0) s_tot[warp] = running;
+    __syncthreads();
+    if (warp == 0) {
+        const long long v = s_tot[lane];
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        s_tot[lane] = incl - v;
+        if (lane == 31) *n_tax_out = incl;
+    }
+    __syncthreads();
+    const long long off = s_tot[warp];
+    if (off != 0)
+        for (long long i = lo + lane; i < hi; i += 32) final_base[i] += off;
+}
+
+// Two-level form for many tiles (the streaming kernel has one per 128 rows): every CTA scans a chunk of 1024 counts
+// (one per thread, coalesced) and records the chunk total; one more tiny launch scans the chunk totals. The final
+// position of tile t is chunk_off[t / 1024] + final_base[t].
+constexpr int kScanChunk = 1024;
+
+__global__ void __launch_bounds__(kScanChunk) counts_scan_local_kernel(const int* __restrict__ tile_cnt, long long n_tiles,
+                                                                       long long* __restrict__ final_base, long long* __restrict__ chunk_tot) {
+    __shared__ long long s_w[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long t = (long long)blockIdx.x * kScanChunk + threadIdx.x;
+    const long long v = t < n_tiles ? (long long)tile_cnt[t] : 0;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const long long w = s_w[lane];
+        long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
+        s_w[lane] = wi - w;
+        if (lane == 31) chunk_tot[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    if (t < n_tiles) final_base[t] = s_w[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(32) counts_scan_chunks_kernel(long long* __restrict__ chunk_tot, long long n_chunks,
+                                                                long long* __restrict__ n_tax_out) {
+    const int lane = threadIdx.x;
+    long long running = 0;
+    for (long long i = 0; i < n_chunks; i += 32) {
+        const long long c = i + lane;
+        const long long v = c < n_chunks ? chunk_tot[c] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (c < n_chunks) chunk_tot[c] = running + incl - v;  // in place: exclusive offsets
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) *n_tax_out = running;
 }
 
 // K1c: move every tile's block of per-TaxID rows from its reserved (unordered) place to input order
@@ -515,6 +572,7 @@ struct CountsPermute {
     long long n_tiles;
     const long long* tile_base;
     const long long* final_base;
+    const long long* chunk_off;  // two-level scan: offset of tile t's chunk (t / kScanChunk), or NULL
     const int* tile_cnt;
     int R;
     const long long* t_tax; long long* out_tax;
@@ -525,20 +583,23 @@ struct CountsPermute {
     const double* t_noise; double* out_noise;
 };
 
-__global__ void __launch_bounds__(128) counts_permute_kernel(const CountsPermute p) {
-    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const int cnt = p.tile_cnt[t];
-        if (cnt == 0) continue;
-        const long long src = p.tile_base[t], dst = p.final_base[t];
-        const int tid = threadIdx.x;
-        if (p.out_tax) for (int i = tid; i < cnt; i += 128) p.out_tax[dst + i] = p.t_tax[src + i];
-        if (p.out_nal) for (int i = tid; i < cnt; i += 128) p.out_nal[dst + i] = p.t_nal[src + i];
-        if (p.out_first) for (int i = tid; i < cnt; i += 128) p.out_first[dst + i] = p.t_first[src + i];
-        const long long nR = (long long)cnt * p.R;
-        if (p.out_k) for (long long i = tid; i < nR; i += 128) p.out_k[dst * p.R + i] = p.t_k[src * p.R + i];
-        if (p.out_N) for (long long i = tid; i < nR; i += 128) p.out_N[dst * p.R + i] = p.t_N[src * p.R + i];
-        if (p.out_noise) for (int i = tid; i < 3 * cnt; i += 128) p.out_noise[dst * 3 + i] = p.t_noise[src * 3 + i];
-    }
+constexpr int kPermuteWarps = 4;
+
+__global__ void __launch_bounds__(kPermuteWarps * 32) counts_permute_kernel(const CountsPermute p) {
+    // one warp per tile: a tile's block is a handful of TaxIDs, so the tiles must move in parallel
+    const int lane = threadIdx.x & 31;
+    const long long t = (long long)blockIdx.x * kPermuteWarps + (threadIdx.x >> 5);
+    if (t >= p.n_tiles) return;
+    const int cnt = p.tile_cnt[t];
+    if (cnt == 0) return;
+    const long long src = p.tile_base[t], dst = p.final_base[t] + (p.chunk_off ? p.chunk_off[t / kScanChunk] : 0);
+    if (p.out_tax) for (int i = lane; i < cnt; i += 32) p.out_tax[dst + i] = p.t_tax[src + i];
+    if (p.out_nal) for (int i = lane; i < cnt; i += 32) p.out_nal[dst + i] = p.t_nal[src + i];
+    if (p.out_first) for (int i = lane; i < cnt; i += 32) p.out_first[dst + i] = p.t_first[src + i];
+    const long long nR = (long long)cnt * p.R;
+    if (p.out_k) for (long long i = lane; i < nR; i += 32) p.out_k[dst * p.R + i] = p.t_k[src * p.R + i];
+    if (p.out_N) for (long long i = lane; i < nR; i += 32) p.out_N[dst * p.R + i] = p.t_N[src * p.R + i];
+    if (p.out_noise) for (int i = lane; i < 3 * cnt; i += 32) p.out_noise[dst * 3 + i] = p.t_noise[src * 3 + i];
 }
 
 // ---------------------------------------------------------------------------------------------
