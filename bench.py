@@ -273,7 +273,7 @@ def counts_stress(ctx, torch, dev, n_rows=10_000_000, reps=5):
             "traffic": ncu_metric("counts", "dram_bytes_per_launch") if n_rows == 10_000_000 else None,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, read by tools/ncu_metrics.py from the committed "
                               "ncu --set full capture (profiles/r02_ncu_metrics.json); null if that file is absent",
-            "kernel": "counts kernels (K1) of one mdg_counts_reduce call", "rows": n_rows, "kept_taxa": int(kept), "kernel_ms": ms,
+            "kernel": "counts_stream_kernel + scans + permute (K1) of one mdg_counts_reduce call", "rows": n_rows, "kept_taxa": int(kept), "kernel_ms": ms,
             "algorithmic_bytes_per_row": ALGO_BYTES_PER_ROW, "peak_source": which,
             "note": "inputs (780 MB) exceed L2; mean of %d calls after 2 warm-ups, CUDA events on the launch stream" % reps}
 
