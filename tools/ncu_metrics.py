@@ -10,7 +10,7 @@ import json
 import subprocess
 import sys
 
-KEYS = {"nuts": "nuts_group_kernel", "counts": "counts_reduce_kernel"}
+KEYS = {"nuts": "nuts_group_kernel", "counts": "counts_stream_kernel"}
 METRICS = {
     "duration_ms": "gpu__time_duration.sum",
     "dram_bytes_read": "dram__bytes_read.sum",
