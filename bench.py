@@ -318,6 +318,8 @@ def main():
     ap.add_argument("--no-counts-stress", action="store_true")
     ap.add_argument("--no-seam", action="store_true")
     ap.add_argument("--no-full-pass", action="store_true", help="skip the 1M-TaxID single pass at N = 8")
+    ap.add_argument("--full-pass-taxa", type=int, default=None,
+                    help="fitted TaxIDs per GPU of the extra single pass (default: 125 000 at N = 8 = BASELINE config 3's 1M TaxIDs, none otherwise)")
     ap.add_argument("--inflight", type=int, default=1, choices=[1, 2], help="batches in flight per GPU (MDG_MAX_INFLIGHT = 2)")
     ap.add_argument("--heuristic", type=int, default=0, help="find_heuristic_step_size (0 = numpyro 0.4.1 default)")
     args = ap.parse_args()
@@ -480,10 +482,10 @@ def main():
 
     # ---------------- N = 8: one full-size pass of BASELINE config 3 (1M TaxIDs over the box) ----------------
     full_pass = None
-    if world == 8 and not args.no_full_pass:
+    n_full = args.full_pass_taxa if args.full_pass_taxa is not None else (1_000_000 // world if world == 8 else 0)
+    if n_full > 0 and not args.no_full_pass:
         del batch, submit_device, submit_reduced
         torch.cuda.empty_cache()
-        n_full = 1_000_000 // world
         gf = workload(args, rank, world, n_fit=n_full)
         bf = DeviceBatch(torch, dev, gf, R, 1)
         submit_full = make_submit_device(bf, cfg)
@@ -494,7 +496,7 @@ def main():
         t_wall = time.perf_counter() - t_wall
         full_pass = {"taxids": int(full_fits), "ms": full_ms, "value": full_fits / (full_ms * 1e-3), "unit": UNIT, "steps": 1,
                      "wall_s_incl_barriers": t_wall, "clocks": fs.stop(),
-                     "what": "ONE pass over 1M fitted TaxIDs (125 000 per GPU, cfg3 generator, seed 20240002, rank r = jumped block r), "
+                     "what": f"ONE pass over {n_full * world} fitted TaxIDs ({n_full} per GPU, cfg3 generator, seed 20240002, rank r = jumped block r), "
                              "device resident, after one untimed pass; max over ranks of the CUDA-event time"}
 
     # ---------------- longest chain (a step's tail is a few sequential Markov chains) ----------------
