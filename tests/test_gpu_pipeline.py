@@ -130,3 +130,27 @@ def test_compute_counts_pieces_and_dense_reuse(tmp_path, oracle):
     want = fits.extract_top_max_fits(df, 37)
     assert np.array_equal(top["tax_id"], want["tax_id"].astype(np.int64).unique())
     assert fits.select_top_dense(df, dense, None) is dense
+
+
+def test_compute_counts_on_two_gpus_equals_one(tmp_path):
+    """cfg.gpus = 2: the file is cut at a TaxID boundary, each GPU tokenises and reduces its piece (own ctx, own host
+    thread, nothing exchanged), the pieces are merged on the host: same df_counts as on one GPU, and the fits of the
+    two-GPU run (TaxID ranges per GPU) equal the one-GPU ones bit for bit. Skipped on single-GPU boxes."""
+    from metadamage_b200 import _lib, counts, fits, synthetic as syn
+
+    if _lib.load().mdg_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = syn.make_mismatch_matrix(0, n_fit=300, seed=11)
+    path = tmp_path / "synth2.txt"
+    syn.write_tsv(g, str(path))
+    cfg1 = make_cfg(tmp_path / "o1")
+    cfg1.add_filename(path)
+    cfg2 = make_cfg(tmp_path / "o2", )
+    cfg2.gpus = 2
+    cfg2.add_filename(path)
+    df1, df2 = counts.compute_counts(cfg1), counts.compute_counts(cfg2)
+    assert df2.equals(df1)
+    kw = dict(progress_bar=False, num_warmup=60, num_samples=80, num_chains=1, chain_method="sequential")
+    r1, p1 = fits.compute_fits(df1, cfg1, kw)
+    r2, p2 = fits.compute_fits(df2, cfg2, kw)
+    assert r2.drop(columns=["shortname"]).equals(r1.drop(columns=["shortname"])) and p2["median"].equals(p1["median"])
