@@ -1,4 +1,5 @@
 """Build libmdgb200.so in-tree with nvcc for sm_100a (B200). No other architecture is built."""
+import glob
 import os
 import shutil
 import subprocess
@@ -8,16 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmdgb200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "mdg_api.cu")]
-HEADERS = [
-    os.path.join(_ROOT, "include", "mdg.h"),
-    os.path.join(_HERE, "csrc", "mdg_common.cuh"),
-    os.path.join(_HERE, "csrc", "mdg_model.cuh"),
-    os.path.join(_HERE, "csrc", "mdg_fit_kernels.cuh"),
-    os.path.join(_HERE, "csrc", "mdg_post_kernels.cuh"),
-    os.path.join(_HERE, "csrc", "mdg_counts_kernel.cuh"),
-    os.path.join(_HERE, "csrc", "mdg_tsv_kernel.cuh"),
-    os.path.join(_HERE, "csrc", "mdg_select_kernel.cuh"),
-]
+HEADERS = [os.path.join(_ROOT, "include", "mdg.h")] + sorted(glob.glob(os.path.join(_HERE, "csrc", "*.cuh")))
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -64,6 +64,8 @@ struct mdg_fit_lane {
     cudaEvent_t ev[5] = {};  // chunk begin, MAP end, NUTS end, predictive end, done (after assembly + D2H)
     cudaEvent_t fork_ev = nullptr, join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     mdg::DevBuf rec, map, pred, counters, samples, waic, waic_acc[4];
+    mdg::DevBuf chain_clock;  // development switch MDG_CHAIN_CLOCK=<file>
+    int clock_items = 0;
     unsigned long long* h_leap = nullptr;  // pinned [MDG_NUM_RUNS]
     bool busy = false;
     int owner = -1;          // ticket slot of the chunk in flight
@@ -178,23 +180,38 @@ int env_int(const char* name, int dflt) {
 }
 
 // K4, group layout: GW lanes per chain, rolled position loop (mdg_nuts_kernel.cuh)
-template <int MODEL, int GW>
+template <int MODEL, int GW, int WARPS>
 int launch_nuts_group(mdg_ctx* ctx, cudaStream_t st, FitLaunch fl, DevBuf& acc) {
-    auto kern = nuts_group_kernel<MODEL, GW, kNutsWarps>;
-    int n_obs = 0;
-    for (int m = fl.mask0; m < fl.mask0 + fl.n_masks; ++m) n_obs = std::max(n_obs, m == 0 ? 2 * fl.P : fl.P);
+    auto kern = nuts_group_kernel<MODEL, GW, WARPS>;
+    const int n_obs = fl.n_items_all > 0 ? 2 * fl.P : fl.P;  // the launch's longest run
     fl.n_slots = (n_obs + 1 + GW - 1) / GW;  // index 0 is the spare
-    const size_t smem = (size_t)kNutsWarps * nuts_warp_smem_bytes(fl.n_slots);
+    size_t smem = (size_t)WARPS * nuts_warp_smem_bytes(fl.n_slots);
+    // The four NUTS launches of a chunk take over each other's CTA slots as CTAs retire. Shared memory is allocated
+    // contiguously, so a retiring CTA's hole must fit the next launch's CTA: every launch asks for the same footprint
+    // (static + dynamic), the largest of the four (PMD, all positions). Otherwise the SMs end up with three resident
+    // CTAs instead of four (chain timeline in profiles/r02_nuts_tuning.md: 8 016 live chains instead of 9 472).
+    if (env_int("MDG_NUTS_UNIFORM_SMEM", 1)) {
+        cudaFuncAttributes mine, big;
+        MDG_CUDA_TRY(cudaFuncGetAttributes(&mine, kern));
+        MDG_CUDA_TRY(cudaFuncGetAttributes(&big, nuts_group_kernel<0, GW, WARPS>));
+        const size_t want = big.sharedSizeBytes + (size_t)WARPS * nuts_warp_smem_bytes((2 * fl.P + 1 + GW - 1) / GW);
+        if (want > mine.sharedSizeBytes + smem) smem = want - mine.sharedSizeBytes;
+    }
     MDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // The same shared-memory carveout for every NUTS kernel: a launch whose preference differs from the previous
+    // launch's is a device-side synchronisation point (the null-model launches used to wait for the LAST chain of the
+    // PMD launches instead of taking over their CTA slots; chain timeline in profiles/r02_nuts_tuning.md).
+    if (env_int("MDG_NUTS_CARVEOUT", 1))
+        MDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // One group slot per item up to the whole GPU. (Smaller grids that leave every group several items were measured:
     // 3 / 6 / 12 items per group cost 14 / 21 / 39 % at 10 000 TaxIDs per batch and 0 / 9 / 35 % at 40 000 — fewer
     // resident chains, and different kernels sharing an SM's instruction cache; profiles/r02_nuts_tuning.md.)
     const int per_group = std::max(1, env_int("MDG_ITEMS_PER_GROUP", 1));
-    const int grid = persistent_grid(kern, kNutsWarps * 32, smem, ctx->num_sms, fl.n_items, kNutsWarps * (32 / GW) * per_group);
-    int rc = acc.ensure((size_t)grid * kNutsWarps * 4 * fl.n_slots * 32 * sizeof(double));
+    const int grid = persistent_grid(kern, WARPS * 32, smem, ctx->num_sms, fl.n_items, WARPS * (32 / GW) * per_group);
+    int rc = acc.ensure((size_t)grid * WARPS * 4 * fl.n_slots * 32 * sizeof(double));
     if (rc) return rc;
     fl.waic_acc = acc.as<double>();
-    kern<<<grid, kNutsWarps * 32, smem, st>>>(fl);
+    kern<<<grid, WARPS * 32, smem, st>>>(fl);
     MDG_CUDA_TRY(cudaGetLastError());
     ctx->timings.n_launches++;
     return MDG_OK;
@@ -202,8 +219,9 @@ int launch_nuts_group(mdg_ctx* ctx, cudaStream_t st, FitLaunch fl, DevBuf& acc) 
 
 template <int MODEL>
 int launch_nuts_group_dispatch(mdg_ctx* ctx, cudaStream_t st, const FitLaunch& fl, DevBuf& acc, int gw) {
-    if (gw == 16) return launch_nuts_group<MODEL, 16>(ctx, st, fl, acc);
-    return launch_nuts_group<MODEL, 8>(ctx, st, fl, acc);
+    if (gw == 16) return launch_nuts_group<MODEL, 16, kNutsWarps>(ctx, st, fl, acc);
+    if (env_int("MDG_NUTS_WARPS", kNutsWarps) == 2) return launch_nuts_group<MODEL, 8, 2>(ctx, st, fl, acc);  // A/B: CTAs of two warps
+    return launch_nuts_group<MODEL, 8, kNutsWarps>(ctx, st, fl, acc);
 }
 
 int launch_map(mdg_ctx* ctx, cudaStream_t st, const MapLaunch& ml, int npl) {
@@ -350,7 +368,7 @@ void mdg_ctx_destroy(mdg_ctx* ctx) {
     if (ctx->inputs_ready) cudaEventDestroy(ctx->inputs_ready);
     for (auto& ln : ctx->lane) {
         for (mdg::DevBuf* b : {&ln.rec, &ln.map, &ln.pred, &ln.counters, &ln.samples, &ln.waic, &ln.waic_acc[0], &ln.waic_acc[1],
-                               &ln.waic_acc[2], &ln.waic_acc[3]})
+                               &ln.waic_acc[2], &ln.waic_acc[3], &ln.chain_clock})
             b->release();
         for (int i = 0; i < 5; ++i) if (ln.ev[i]) cudaEventDestroy(ln.ev[i]);
         if (ln.fork_ev) cudaEventDestroy(ln.fork_ev);
@@ -1016,6 +1034,12 @@ int harvest_lane(mdg_ctx* ctx, mdg_fit_lane& ln) {
     if (!tk.have_nuts) { tk.nuts_begin_ms = a; tk.nuts_end_ms = b; tk.have_nuts = true; }
     tk.nuts_begin_ms = std::min(tk.nuts_begin_ms, a);
     tk.nuts_end_ms = std::max(tk.nuts_end_ms, b);
+    if (ln.clock_items > 0) {  // development: append this chunk's per-chain start / end times to the file MDG_CHAIN_CLOCK names
+        std::vector<unsigned long long> h((size_t)ln.clock_items * 2);
+        MDG_CUDA_TRY(cudaMemcpy(h.data(), ln.chain_clock.ptr, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(getenv("MDG_CHAIN_CLOCK"), "ab")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        ln.clock_items = 0;
+    }
     ln.busy = false;
     ln.owner = -1;
     return MDG_OK;
@@ -1187,6 +1211,12 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
         fl.da_sqrt = ctx->da_tables.as<double>(); fl.da_pow = fl.da_sqrt + kDaTable;
         fl.trace = d_trace ? d_trace + (size_t)c0 * MDG_NUM_RUNS * (W + S) * 4 : nullptr;
         for (int r = 0; r < MDG_NUM_RUNS; ++r) fl.sample_slot[r] = out_samples ? r : ((r & 1) ? -1 : r / 2);
+        if (getenv("MDG_CHAIN_CLOCK")) {
+            if ((rc = ln.chain_clock.ensure((size_t)chunk_max * MDG_NUM_RUNS * 16))) return bail(rc);
+            MDG_CUDA_TRY(cudaMemsetAsync(ln.chain_clock.ptr, 0, (size_t)nc * MDG_NUM_RUNS * 16, ls));
+            fl.chain_clock = ln.chain_clock.as<unsigned long long>();
+            ln.clock_items = nc * MDG_NUM_RUNS;
+        }
         // Overlap with the chunk in flight on another lane is wanted for its TAIL only (a few long chains on an
         // otherwise idle GPU), not for its bulk: two different NUTS kernels sharing the SMs evict each other from
         // the instruction cache (measured: -2..-5 % with unrestricted overlap). So this chunk's NUTS launches wait
@@ -1203,17 +1233,32 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
             // PMD chains are long and heavy-tailed (adapted step size; max ~8x the mean), null chains
             // short and uniform: PMD first, null last fills the tail (profiles/r01_nuts_tuning.md).
             FitLaunch a = fl;  // PMD, all positions
-            a.n_masks = 1; a.mask0 = 0; a.n_items = nc; a.work_counter = d_counters + 1;
-            FitLaunch b = fl;  // null, all positions
-            b.n_masks = 1; b.mask0 = 0; b.n_items = nc; b.work_counter = d_counters + 2;
+            a.n_items = nc; a.n_items_all = nc; a.work_counter = d_counters + 1;
+            FitLaunch b = a;   // null, all positions
+            b.work_counter = d_counters + 2;
             FitLaunch c = fl, d = fl;  // PMD / null, forward-only and reverse-only
             c.work_counter = d_counters + 3; d.work_counter = d_counters + 4;
-            c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_masks = 2; d.n_masks = 2; c.mask0 = 1; d.mask0 = 1;
+            c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_items_all = 0; d.n_items_all = 0;
             const int gw_all = env_int("MDG_GW_ALL", 8), gw_half = env_int("MDG_GW_HALF", 8);  // lanes per chain (A/B runs: 16)
-            if (fwd_rev && (rc = launch_nuts_group_dispatch<0>(ctx, ln.side[1], c, ln.waic_acc[2], gw_half))) return bail(rc);
-            if ((rc = launch_nuts_group_dispatch<0>(ctx, ln.side[3], a, ln.waic_acc[0], gw_all))) return bail(rc);
-            if (fwd_rev && (rc = launch_nuts_group_dispatch<1>(ctx, ln.side[2], d, ln.waic_acc[3], gw_half))) return bail(rc);
-            if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
+            if (fwd_rev && env_int("MDG_NUTS_MERGE", 1)) {
+                // One launch and ONE queue per model: the all-position runs first (the longest chains), then the
+                // forward-only / reverse-only runs. A group that finishes a chain always finds the next item until the
+                // model's whole queue is empty, so the only hand-over between launches (CTA slots are released per CTA,
+                // i.e. when the last of its 16 chains ends) is PMD -> null.
+                a.n_items = 3 * nc; b.n_items = 3 * nc;
+                if ((rc = launch_nuts_group_dispatch<0>(ctx, ln.side[3], a, ln.waic_acc[0], gw_all))) return bail(rc);
+                if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
+            } else if (env_int("MDG_NUTS_A_FIRST", 1)) {
+                if ((rc = launch_nuts_group_dispatch<0>(ctx, ln.side[3], a, ln.waic_acc[0], gw_all))) return bail(rc);
+                if (fwd_rev && (rc = launch_nuts_group_dispatch<0>(ctx, ln.side[1], c, ln.waic_acc[2], gw_half))) return bail(rc);
+                if (fwd_rev && (rc = launch_nuts_group_dispatch<1>(ctx, ln.side[2], d, ln.waic_acc[3], gw_half))) return bail(rc);
+                if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
+            } else {
+                if (fwd_rev && (rc = launch_nuts_group_dispatch<0>(ctx, ln.side[1], c, ln.waic_acc[2], gw_half))) return bail(rc);
+                if ((rc = launch_nuts_group_dispatch<0>(ctx, ln.side[3], a, ln.waic_acc[0], gw_all))) return bail(rc);
+                if (fwd_rev && (rc = launch_nuts_group_dispatch<1>(ctx, ln.side[2], d, ln.waic_acc[3], gw_half))) return bail(rc);
+                if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
+            }
         }
         for (int i = 0; i < 4; ++i) {
             MDG_CUDA_TRY(cudaEventRecord(ln.join_ev[i], ln.side[i]));

@@ -151,6 +151,12 @@ __device__ __forceinline__ void log_table_init() {
     __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // 1/x for positive normal x: hardware seed (MUFU.RCP64H, ~2^-21) + two Newton steps (<= 2 ulp)
 __device__ __forceinline__ double rcp_pos(double x) {
     double r;

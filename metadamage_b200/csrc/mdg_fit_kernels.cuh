@@ -28,19 +28,19 @@ struct FitLaunch {
     int n_windows;
     int win_end[kMaxWindows];
     unsigned int* work_counter;
-    int n_items;
-    int n_masks;        // lane masks handled per TaxID by this launch (1: all positions; 2: forward-only and reverse-only)
-    int mask0;          // first mask of this launch
+    int n_items;        // items [0, n_items_all) are all-position runs (TaxID = item), the rest forward-only / reverse-only
+    int n_items_all;    // runs (TaxID = (item - n_items_all) / 2, mask 1 + (item - n_items_all) % 2): ONE queue, long chains first
     RunRecord* rec;     // [n_tax][6]
     double* waic;       // [n_tax][6][2][2P]: lppd_i, pWAIC_i
     double* samples;    // [n_tax][sample_runs][S][4] constrained draws, or NULL
     int sample_slot[MDG_NUM_RUNS];  // run kind -> slot in `samples`, -1 = not stored
     int sample_runs;
     double* trace;      // [n_tax][6][W+S][4] or NULL
-    int n_slots;        // rounds of the position loop, ceil((n_obs + 1) / GW)
+    int n_slots;        // rounds of the position loop of the launch's longest run, ceil((n_obs + 1) / GW): shared-memory layout
     const double* da_sqrt;  // [kDaTable] sqrt(t)
     const double* da_pow;   // [kDaTable] t^-0.75 (dual averaging, hmc_util.dual_averaging kappa)
     double* waic_acc;   // WAIC accumulators, [grid * warps][4][n_slots][32]
+    unsigned long long* chain_clock;  // development (MDG_CHAIN_CLOCK): [n_tax][6][2] globaltimer at chain start / end, or NULL
 };
 
 template <int D>

@@ -234,10 +234,10 @@ __device__ __forceinline__ void eval_group(const double2* __restrict__ kn, doubl
 }
 
 #ifndef MDG_NUTS_MINBLOCKS
-#define MDG_NUTS_MINBLOCKS 4  // 128 registers per thread, 16 warps per SM (3 / 5 / 6 were measured slower: profiles/r01_nuts_tuning.md)
+#define MDG_NUTS_MINBLOCKS 4  // CTAs of four warps per SM: 128 registers per thread, 16 warps per SM (3 / 5 / 6 were measured slower: profiles/r01_nuts_tuning.md)
 #endif
 template <int MODEL, int GW, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_kernel(const FitLaunch p) {
+__global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS * 4 / WARPS) nuts_group_kernel(const FitLaunch p) {
     constexpr int D = ModelDim<MODEL>::value;
     constexpr int GROUPS = 32 / GW;
     __shared__ GroupShared<D> sh_all[WARPS * GROUPS];
@@ -253,7 +253,9 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
     double2* const kn = reinterpret_cast<double2*>(wbase);                        // [NS][32]
     double* const llb = reinterpret_cast<double*>(wbase + (size_t)NS * 32 * 16);  // [4][NS][32]
     // WAIC accumulators of this lane (touched once per kept draw): global scratch, [4][NS][32] per warp
-    double* const wacc = p.waic_acc + ((size_t)blockIdx.x * WARPS + warp) * 4 * (size_t)NS * 32 + lane;
+    // (the address is recomputed where it is used — chain start, kept draw, chain end — instead of being carried
+    // through the leapfrog loop in two registers)
+    auto wacc_of_lane = [&]() { return p.waic_acc + ((size_t)blockIdx.x * WARPS + warp) * 4 * (size_t)NS * 32 + lane; };
     const size_t wstride = (size_t)NS * 32;
 
     const int W = p.cfg.num_warmup, S = p.cfg.num_samples, P = p.P;
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
     // ---- per-chain state in registers (group-uniform) ----
     int phase = GP_FETCH;
     int tax = 0, mask = 0, run_kind = 0, n_obs = 0;
+    int ns = 0;  // rounds of the position loop of THIS chain (<= NS, the launch's layout)
     uint2 key = make_uint2(0u, 0u);
     LlRoles roles;
     roles.v = 0xE4u;  // identity: role f -> buffer f
@@ -383,13 +386,22 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
             if (item >= (unsigned)p.n_items) {
                 phase = GP_IDLE;
             } else {
-                tax = (int)(item / (unsigned)p.n_masks);
-                mask = p.mask0 + (int)(item % (unsigned)p.n_masks);
+                if (item < (unsigned)p.n_items_all) {
+                    tax = (int)item;
+                    mask = 0;
+                } else {
+                    const unsigned h = item - (unsigned)p.n_items_all;
+                    tax = (int)(h >> 1);
+                    mask = 1 + (int)(h & 1u);
+                }
                 run_kind = mask * 2 + MODEL;
                 n_obs = mask == 0 ? 2 * P : P;
+                ns = (n_obs + GW) / GW;  // index 0 is the spare
                 key = make_key(p.cfg.seed, p.tax_id[tax]);
+                if (p.chain_clock != nullptr && lig == 0) p.chain_clock[((size_t)tax * MDG_NUM_RUNS + run_kind) * 2] = global_timer_ns();
                 const uint32_t* kk = p.k + (size_t)tax * 2 * P + (mask == 2 ? P : 0);
                 const uint32_t* NN = p.N + (size_t)tax * 2 * P + (mask == 2 ? P : 0);
+                double* const wacc = wacc_of_lane();
 #pragma unroll 1
                 for (int s = 0; s < NS; ++s) {
                     const int j = s * GW + lig - 1;
@@ -439,7 +451,7 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
             // shared memory: the evaluation's interleaved special-function chains get the registers
 #pragma unroll
             for (int j = 0; j < D; ++j) { sh.zn_park[j] = zn[j]; sh.rh_park[j] = rh[j]; }
-            eval_group<MODEL, GW>(kn, llb + (size_t)roles.get(LL_X) * wstride, NS, lane, lig, gmask, P, mask, n_obs, zn, sh_prior,
+            eval_group<MODEL, GW>(kn, llb + (size_t)roles.get(LL_X) * wstride, ns, lane, lig, gmask, P, mask, n_obs, zn, sh_prior,
                                   phi_min, logp, grad, valid);
             __syncwarp(gmask);
 #pragma unroll
@@ -658,8 +670,9 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
                             __syncwarp(gmask);
                             // WAIC: streaming logsumexp + Welford of this lane's log-likelihoods (fits.py:147-165)
                             const double* llc = llb + (size_t)roles.get(LL_CUR) * wstride + lane;
+                            double* const wacc = wacc_of_lane();
 #pragma unroll 1
-                            for (int s = 0; s < NS; ++s) {
+                            for (int s = 0; s < ns; ++s) {
                                 const double v = llc[s * 32];
                                 double wmax = wacc[0 * wstride + s * 32], wsum = wacc[1 * wstride + s * 32];
                                 double wmean = wacc[2 * wstride + s * 32], wm2 = wacc[3 * wstride + s * 32];
@@ -738,8 +751,9 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
             double waic_sum = 0.0, lppd_sum = 0.0;
             const size_t R = 2 * (size_t)P;
             double* wout = p.waic + ((size_t)tax * MDG_NUM_RUNS + run_kind) * 2 * R;
+            double* const wacc = wacc_of_lane();
 #pragma unroll 1
-            for (int s = 0; s < NS; ++s) {
+            for (int s = 0; s < ns; ++s) {
                 const int j = s * GW + lig - 1;
                 if ((unsigned)j < (unsigned)n_obs && !failed && S > 0) {
                     const double2 d = kn[s * 32 + lane];
@@ -768,8 +782,13 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS) nuts_group_ker
                 for (int j = 0; j < 5; ++j) { r.mean[j] = sh.acc_mean[j]; r.sd[j] = S > 0 ? sqrt(sh.acc_m2[j] / (double)S) : 0.0; }
                 r.failed = (uint32_t)failed;
                 r.pad = 0;
+                if (p.chain_clock != nullptr) p.chain_clock[((size_t)tax * MDG_NUM_RUNS + run_kind) * 2 + 1] = global_timer_ns();
             }
             __syncwarp(gmask);
+            // the leapfrog source is dead here; saying so keeps it from being carried (spilled: 48 B of local memory
+            // in the PMD kernel) across the evaluation for the paths that end a chain without overwriting it
+#pragma unroll
+            for (int j = 0; j < D; ++j) { zf[j] = 0.0; rf[j] = 0.0; gf[j] = 0.0; }
             phase = GP_FETCH;
         }
     }
