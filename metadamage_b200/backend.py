@@ -28,6 +28,19 @@ def _dptr(t, rows_ok=False):
     return C.c_void_p(t.data_ptr())
 
 
+def _text_arg(text):
+    """bytes-like or a contiguous uint8 ndarray (e.g. counts.read_file_bytes' pinned buffer) -> (ctypes argument, length,
+    keep-alive object)"""
+    if isinstance(text, np.ndarray):
+        if text.dtype != np.uint8 or not text.flags["C_CONTIGUOUS"]:
+            raise TypeError("text array must be contiguous uint8")
+        return C.cast(text.ctypes.data, C.c_char_p), int(text.size), text
+    if not isinstance(text, (bytes, bytearray, memoryview)):
+        raise TypeError("text must be bytes or a uint8 array")
+    b = bytes(text)
+    return b, len(b), b
+
+
 class Context:
     """One GPU, one stream. Not thread-safe; use one Context per host thread / process."""
 
@@ -83,16 +96,14 @@ class Context:
     # ------------------------------------------------------------------ K0
     def tsv_parse(self, text, want_spans=False):
         """Tokenise a mismatch-matrix file (bytes) on the GPU -> SoA numpy columns (counts.py:229-235)."""
-        if not isinstance(text, (bytes, bytearray, memoryview)):
-            raise TypeError("text must be bytes")
-        text = bytes(text)
-        cap = text.count(b"\n") + 1
+        arg, n_bytes, _keep = _text_arg(text)
+        cap = (int(np.count_nonzero(text == 10)) if isinstance(text, np.ndarray) else _keep.count(b"\n")) + 1
         out = dict(tax_id=np.empty(cap, np.int64), n_alignments=np.empty(cap, np.uint32), is_reverse=np.empty(cap, np.uint8),
                    pos0=np.empty(cap, np.uint8), counts16=np.empty((16, cap), np.uint32),
                    name_span=np.empty((cap, 2), np.int64) if want_spans else None,
                    rank_span=np.empty((cap, 2), np.int64) if want_spans else None)
         n_rows, n_cols = C.c_int64(0), C.c_int32(0)
-        _lib.check(self._lib.mdg_tsv_parse(self._h, MDG_HOST, text, len(text), cap, ptr(out["tax_id"]), ptr(out["n_alignments"]),
+        _lib.check(self._lib.mdg_tsv_parse(self._h, MDG_HOST, arg, n_bytes, cap, ptr(out["tax_id"]), ptr(out["n_alignments"]),
                                            ptr(out["is_reverse"]), ptr(out["pos0"]), ptr(out["counts16"]), cap,
                                            ptr(out["name_span"]), ptr(out["rank_span"]), C.byref(n_rows), C.byref(n_cols)))
         n = n_rows.value
@@ -107,12 +118,10 @@ class Context:
         `rank_span` ([rows][2] int64, 22-column layout) when asked for."""
         import torch
 
-        if not isinstance(text, (bytes, bytearray, memoryview)):
-            raise TypeError("text must be bytes")
-        text = bytes(text)
+        arg, n_bytes, _keep = _text_arg(text)
         # room for the rows without counting the newlines on the host (70 ms per 100 MB): a data line is at least
         # 39 bytes long (20 fields, 19 tabs, newline, an empty strand field at worst; 22-column lines are longer still)
-        cap = len(text) // 38 + 2
+        cap = n_bytes // 38 + 2
         dev = torch.device("cuda", self.device)
         cols = dict(tax_id=torch.empty(cap, dtype=torch.int64, device=dev), n_alignments=torch.empty(cap, dtype=torch.int32, device=dev),
                     is_reverse=torch.empty(cap, dtype=torch.uint8, device=dev), pos0=torch.empty(cap, dtype=torch.uint8, device=dev),
@@ -121,7 +130,7 @@ class Context:
             cols["name_span"] = torch.empty((cap, 2), dtype=torch.int64, device=dev)
             cols["rank_span"] = torch.empty((cap, 2), dtype=torch.int64, device=dev)
         n_rows, n_cols = C.c_int64(0), C.c_int32(0)
-        _lib.check(self._lib.mdg_tsv_parse(self._h, MDG_DEVICE, text, len(text), cap, _dptr(cols["tax_id"]), _dptr(cols["n_alignments"]),
+        _lib.check(self._lib.mdg_tsv_parse(self._h, MDG_DEVICE, arg, n_bytes, cap, _dptr(cols["tax_id"]), _dptr(cols["n_alignments"]),
                                            _dptr(cols["is_reverse"]), _dptr(cols["pos0"]), _dptr(cols["counts16"]), cap,
                                            _dptr(cols.get("name_span")), _dptr(cols.get("rank_span")), C.byref(n_rows), C.byref(n_cols)))
         n = n_rows.value

@@ -84,16 +84,59 @@ def reference_row_order(n_alignments, tax_id, z):
     return np.lexsort((-order, -tax_id.astype(np.int64), -n_alignments.astype(np.int64)))
 
 
+def _as_byte_array(text):
+    """bytes-like or uint8 ndarray -> uint8 ndarray (no copy)"""
+    return text if isinstance(text, np.ndarray) else np.frombuffer(text, dtype=np.uint8)
+
+
 def _decode_spans(text, spans):
-    """(offset, length) byte spans -> list of str, decoding each distinct byte string once."""
-    cache, out = {}, []
-    for o, n in spans:
-        b = text[int(o):int(o) + int(n)]
-        v = cache.get(b)
-        if v is None:
-            v = cache[b] = b.decode("utf-8", "replace")
-        out.append(v)
-    return out
+    """(offset, length) byte spans of the file text -> list of str. The spans are gathered into one [n][longest]
+    byte matrix and decoded in one go (ASCII) or string by string (anything else: UTF-8 with replacement)."""
+    spans = np.asarray(spans, dtype=np.int64).reshape(-1, 2)
+    if len(spans) == 0:
+        return []
+    buf = _as_byte_array(text)
+    off, length = spans[:, 0], spans[:, 1]
+    longest = int(length.max())
+    if longest == 0:
+        return [""] * len(spans)
+    col = np.arange(longest, dtype=np.int64)[None, :]
+    idx = np.minimum(off[:, None] + col, len(buf) - 1)
+    mat = buf[idx]
+    mat[col >= length[:, None]] = 0
+    if mat.max() < 128 and not ((mat == 0) & (col < length[:, None])).any():
+        return mat.view(f"S{longest}").ravel().astype(f"U{longest}").astype(object).tolist()
+    raw = bytes(memoryview(buf))
+    return [raw[int(o):int(o) + int(n)].decode("utf-8", "replace") for o, n in zip(off, length)]
+
+
+_TEXT_STAGE = {}  # one reusable page-locked staging buffer per process for the file text
+
+
+def read_file_bytes(filename):
+    """The file as a uint8 array in a reusable PINNED buffer: no fresh 100 MB allocation per file (page faults were
+    two thirds of the read time) and the copy to the GPU is a plain DMA. Valid until the next call."""
+    import os
+
+    size = os.path.getsize(filename)
+    stage = _TEXT_STAGE.get("buf")
+    if stage is None or len(stage) < size:
+        try:
+            import torch
+
+            stage = torch.empty(max(size + size // 4, 1 << 20), dtype=torch.uint8, pin_memory=torch.cuda.is_available()).numpy()
+        except Exception:  # no torch / no CUDA runtime: ordinary memory
+            stage = np.empty(max(size + size // 4, 1 << 20), dtype=np.uint8)
+        _TEXT_STAGE["buf"] = stage
+    view = stage[:size]
+    got = 0
+    with open(filename, "rb", buffering=0) as fh:
+        while got < size:
+            n = fh.readinto(memoryview(view[got:]))
+            if not n:
+                break
+            got += n
+    return view[:got]
 
 
 def read_mismatch_table_gpu(filename, ctx):
@@ -101,8 +144,7 @@ def read_mismatch_table_gpu(filename, ctx):
     (mdg_tsv_parse, K0) instead of by pandas; the two string columns of the 22-column layout are
     cut out of the file bytes through the (offset, length) spans the kernel returns, decoded once per
     run of equal spans' bytes (rows of a TaxID share name and rank)."""
-    with open(filename, "rb") as fh:
-        text = fh.read()
+    text = read_file_bytes(filename)
     r = ctx.tsv_parse(text, want_spans=True)
     logger.info("tsv: %d bytes -> %d rows (parse kernels %.3f ms)", len(text), r["n_rows"], ctx.timings()["counts_ms"])
     data = {"tax_id": r["tax_id"]}
@@ -125,26 +167,43 @@ def read_mismatch_table_gpu(filename, ctx):
     return df
 
 
+def _find_byte(buf, byte, start, stop=None):
+    """index of the first `byte` in buf[start:stop], or -1 (scanned in 64 KB windows)"""
+    stop = len(buf) if stop is None else stop
+    while start < stop:
+        end = min(start + (1 << 16), stop)
+        hit = np.flatnonzero(buf[start:end] == byte)
+        if len(hit):
+            return start + int(hit[0])
+        start = end
+    return -1
+
+
 def split_text_at_taxid_boundaries(text, n_parts):
     """Cut the file bytes into <= n_parts pieces whose first line starts a new TaxID (K1 is
     partitioned at segment boundaries, so no TaxID spans two GPUs and nothing is exchanged). A nominal cut
     at k/n of the bytes is moved forward to the next line whose first field differs from the line before."""
-    n = len(text)
+    buf = _as_byte_array(text)
+    n = len(buf)
     if n_parts <= 1 or n < 1 << 16:
         return [(0, n)]
+    NL, TAB = 10, 9
     cuts = [0]
     for k in range(1, n_parts):
-        pos = text.find(b"\n", max(cuts[-1], (n * k) // n_parts))
+        pos = _find_byte(buf, NL, max(cuts[-1], (n * k) // n_parts))
         if pos < 0:
             break
         pos += 1
-        prev_start = text.rfind(b"\n", 0, pos - 1) + 1
-        prev_id = text[prev_start:text.find(b"\t", prev_start)]
+        back = np.flatnonzero(buf[max(0, pos - 1 - (1 << 16)):pos - 1] == NL)  # start of the line before the cut
+        prev_start = max(0, pos - 1 - (1 << 16)) + int(back[-1]) + 1 if len(back) else (0 if pos - 1 <= (1 << 16) else -1)
+        if prev_start < 0:
+            break  # a line longer than 64 KB: not a mismatch table
+        prev_id = buf[prev_start:_find_byte(buf, TAB, prev_start)]
         while pos < n:
-            tab = text.find(b"\t", pos)
-            if tab < 0 or text[pos:tab] != prev_id:
+            tab = _find_byte(buf, TAB, pos, min(n, pos + (1 << 16)))
+            if tab < 0 or not np.array_equal(buf[pos:tab], prev_id):
                 break
-            nxt = text.find(b"\n", pos)
+            nxt = _find_byte(buf, NL, pos)
             if nxt < 0:
                 pos = n
                 break
@@ -268,7 +327,7 @@ def _assemble_df_counts(pieces, cfg):
         raise AssertionError("Dataframe contains too large values.")  # utils.py:338-339
     data["y_sum_total"] = rows["y_sum_total"].astype(np.uint32)
     data["shortname"] = pd.Categorical.from_codes(np.zeros(n_rows, np.int8), categories=[cfg.shortname])
-    df = pd.DataFrame(data)  # every column already has its final dtype (utils.downcast_dataframe would change nothing)
+    df = pd.DataFrame(data, copy=False)  # every column already has its final dtype (utils.downcast_dataframe would change nothing)
     # K1's dense per-TaxID outputs are remembered for this very DataFrame object (df_counts order), so that
     # compute_fits does not rebuild them from the rows
     first_row = np.r_[0, np.cumsum(seg_len)[:-1]].astype(np.int64) if n_tax else np.zeros(0, np.int64)
@@ -283,8 +342,7 @@ def compute_counts(cfg, df_in=None, ctx=None):
     device(s), only the kept rows return to the host. With cfg.gpus > 1 the file is cut at TaxID boundaries and
     every GPU handles one piece (no exchange)."""
     if df_in is None:
-        with open(cfg.filename, "rb") as fh:
-            text = fh.read()
+        text = read_file_bytes(cfg.filename)
         n_gpus = max(1, min(int(getattr(cfg, "gpus", 1) or 1), _lib_device_count()))
         spans = split_text_at_taxid_boundaries(text, n_gpus) if ctx is None else [(0, len(text))]
         from .parallel import run_on_gpus
