@@ -104,47 +104,75 @@ def select_top_dense(df_counts, dense, n_fits, ctx=None):
     return out
 
 
+def _category_of(values):
+    """what Series.astype("category") builds (sorted distinct values + codes), from one np.unique"""
+    values = np.asarray(values)
+    uniq, inv = np.unique(values, return_inverse=True)
+    return uniq, inv.astype(np.int32 if len(uniq) > 32767 else (np.int16 if len(uniq) > 127 else np.int8))
+
+
+def _final_dtype(arr, col):
+    """utils.downcast_dataframe's rule, applied while the column is built: integers -> uint32 (position -> int8,
+    with its overflow check), floats -> float32"""
+    arr = np.asarray(arr)
+    if arr.dtype.kind in "iu":
+        if len(arr) and arr.max() > np.iinfo("uint32").max:
+            raise AssertionError("Dataframe contains too large values.")
+        return arr.astype("int8" if col == "position" else "uint32", copy=False)
+    if arr.dtype.kind == "f":
+        return arr.astype("float32", copy=False)
+    return arr
+
+
 def make_df_fit_results(res, dense, cfg):
     """fits.py:668-680: one row per fitted TaxID in df_counts order; failed fits are dropped
-    with a warning, like the reference's timed-out fits (fits.py:520-521, 603-606)."""
+    with a warning, like the reference's timed-out fits (fits.py:520-521, 603-606). Every column is built in its
+    final dtype (what utils.downcast_dataframe(df, [tax_id, tax_name, tax_rank, shortname]) gives)."""
     ok = (res["status"] & FIT_FAILED) == 0
     for tax in dense["tax_id"][~ok]:
         logger.warning("Fit: no valid fit for tax_id %s. Skipping for now", tax)
+    n = int(ok.sum())
     data = {}
     for col in FIT_RESULT_COLUMNS:
-        if col in ("tax_name", "tax_rank", "N_alignments"):
-            data[col] = dense[col][ok]
-        elif col == "tax_id":
-            data[col] = dense["tax_id"][ok]
+        if col in ("tax_id", "tax_name", "tax_rank"):
+            vals = dense[col][ok]
+            if col == "tax_id" and n:
+                uniq, codes = _category_of(vals)
+                data[col] = pd.Categorical.from_codes(codes, categories=uniq)
+            else:
+                data[col] = pd.Categorical(np.asarray(vals, dtype=np.int64 if col == "tax_id" else object))
+        elif col == "N_alignments":
+            data[col] = _final_dtype(dense[col][ok], col)
         else:
-            data[col] = res[col][ok]
-    df = pd.DataFrame(data, columns=FIT_RESULT_COLUMNS)
-    df["shortname"] = cfg.shortname
-    df = utils.downcast_dataframe(df, ["tax_id", "tax_name", "tax_rank", "shortname"])
-    return df.reset_index(drop=True), ok
+            data[col] = _final_dtype(res[col][ok], col)
+    data["shortname"] = pd.Categorical.from_codes(np.zeros(n, np.int8), categories=[cfg.shortname])
+    return pd.DataFrame(data, copy=False), ok
 
 
 def make_df_fit_predictions(out, dense, ok, cfg):
-    """fits.py:632-665: 2P rows per TaxID: tax_id, position, median, hdpi_lower, hdpi_upper (sic)."""
+    """fits.py:632-665: 2P rows per TaxID: tax_id, position, median, hdpi_lower, hdpi_upper (sic); final dtypes
+    (category, int8, float32) built directly instead of through a 2P-times-longer object / float64 frame."""
     P = int(cfg.max_position)
-    z = np.arange(P) + 1
+    z = np.arange(P, dtype=np.int8) + 1
     position = np.concatenate([z, -z])
     n = int(ok.sum())
-    df = pd.DataFrame({
-        "tax_id": np.repeat(dense["tax_id"][ok], 2 * P),
+    uniq, codes = _category_of(dense["tax_id"][ok]) if n else (np.zeros(0, np.int64), np.zeros(0, np.int8))
+    return pd.DataFrame({
+        "tax_id": pd.Categorical.from_codes(np.repeat(codes, 2 * P), categories=uniq),
         "position": np.tile(position, n),
-        "median": out["median"][ok].astype(np.float64).ravel(),
-        "hdpi_lower": out["hpdi_lo"][ok].astype(np.float64).ravel(),
-        "hdpi_upper": out["hpdi_hi"][ok].astype(np.float64).ravel(),
-    })
-    df["shortname"] = cfg.shortname
-    return utils.downcast_dataframe(df, ["tax_id", "shortname"])
+        "median": np.ascontiguousarray(out["median"][ok], dtype=np.float32).ravel(),
+        "hdpi_lower": np.ascontiguousarray(out["hpdi_lo"][ok], dtype=np.float32).ravel(),
+        "hdpi_upper": np.ascontiguousarray(out["hpdi_hi"][ok], dtype=np.float32).ravel(),
+        "shortname": pd.Categorical.from_codes(np.zeros(n * 2 * P, np.int8), categories=[cfg.shortname]),
+    }, copy=False)
 
 
 def make_df_fit_map(res, dense, ok, cfg):
-    df = pd.DataFrame({"tax_id": dense["tax_id"][ok], **{c: res[c][ok] for c in FIT_MAP_COLUMNS}})
-    df["shortname"] = cfg.shortname
-    return utils.downcast_dataframe(df, ["tax_id", "shortname"])
+    n = int(ok.sum())
+    uniq, codes = _category_of(dense["tax_id"][ok]) if n else (np.zeros(0, np.int64), np.zeros(0, np.int8))
+    data = {"tax_id": pd.Categorical.from_codes(codes, categories=uniq), **{c: _final_dtype(res[c][ok], c) for c in FIT_MAP_COLUMNS}}
+    data["shortname"] = pd.Categorical.from_codes(np.zeros(n, np.int8), categories=[cfg.shortname])
+    return pd.DataFrame(data, copy=False)
 
 
 def compute_fits(df_counts, cfg, mcmc_kwargs=None, return_map=False, n_fits=None):
