@@ -17,8 +17,10 @@ All K steps are inside the timed region and the last one is drained before the c
 Workload: N = 1 -> BASELINE config 2 (10 000 fitted TaxIDs, seed 20240001, +-15 positions).
           N > 1 -> BASELINE config 3's generator (seed 20240002, min-alignments 10, min-y-sum 10), partitioned
                    by TaxID over the GPUs: rank r fits its own contiguous share (`--taxa-per-gpu`, default
-                   40 000; the r-th jumped Philox block of the seed); at N = 8 one additional full-size pass
-                   (125 000 TaxIDs per GPU = 1M TaxIDs) is timed on its own and reported under `cfg3_full_pass`.
+                   125 000 = 1M / 8; the r-th jumped Philox block of the seed), so at N = 8 every step IS one pass
+                   over config 3's 1M TaxIDs (`cfg3_full_pass` repeats that reading of the line; with another
+                   `--taxa-per-gpu` the full-size pass is timed on its own). Batches of that size also keep the
+                   workload's straggler chains (up to 850 000 leapfrogs in one run; mean 9 800) inside the step.
 
   value            whole-job fits/s with inputs resident in HBM (device pointers through the C-ABI)
   e2e              the same through the host-buffer C-ABI calls (pinned host inputs and outputs, H2D + D2H
@@ -207,7 +209,7 @@ def run_reference(args):
         return
     world = max(1, args.gpus)
     if world > 1 and args.taxa_per_gpu is None:
-        args.taxa_per_gpu = 40_000
+        args.taxa_per_gpu = 125_000
     args.taxa_per_gpu = args.taxa_per_gpu or 10_000
     cores = args.max_cores or os.cpu_count() or 1
     # the sample is drawn from rank 0's share of the GPU arm's workload; a bounded share is enough to draw it from
@@ -311,7 +313,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--taxa-per-gpu", type=int, default=None,
-                    help="fitted TaxIDs per GPU per step (default: 10 000 = cfg2 on 1 GPU, 40 000 of cfg3's generator on N > 1)")
+                    help="fitted TaxIDs per GPU per step (default: 10 000 = cfg2 on 1 GPU, 125 000 = 1M / 8 of cfg3's generator on N > 1)")
     ap.add_argument("--max-position", type=int, default=15)
     ap.add_argument("--max-cores", type=int, default=0, help="host threads of the CPU arm (default: all; the reference CLI's --max-cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -339,7 +341,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.taxa_per_gpu is None:
-        args.taxa_per_gpu = 10_000 if world == 1 else 40_000
+        args.taxa_per_gpu = 10_000 if world == 1 else 125_000
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -483,7 +485,8 @@ def main():
     # ---------------- N = 8: one full-size pass of BASELINE config 3 (1M TaxIDs over the box) ----------------
     full_pass = None
     n_full = args.full_pass_taxa if args.full_pass_taxa is not None else (1_000_000 // world if world == 8 else 0)
-    if n_full > 0 and not args.no_full_pass:
+    steps_are_full_passes = n_full > 0 and n_full == args.taxa_per_gpu
+    if n_full > 0 and not args.no_full_pass and not steps_are_full_passes:
         del batch, submit_device, submit_reduced
         torch.cuda.empty_cache()
         gf = workload(args, rank, world, n_fit=n_full)
@@ -529,7 +532,7 @@ def main():
             "traffic": ncu_metric("nuts", "dram_bytes_per_launch"),
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one NUTS launch, read by tools/ncu_metrics.py from the committed "
                               "ncu --set full capture (profiles/r02_ncu_metrics.json); null if that file is absent",
-            "kernel": "nuts_group_kernel<PMD|null, 8 lanes per chain> (4 launches per batch)",
+            "kernel": "nuts_group_kernel<PMD|null, 8 lanes per chain> (one launch and one queue per model and batch)",
             "flop_model": "SURVEY.md 8d nominal: PMD 300*n_obs+55, null 190*n_obs+165 flop per gradient evaluation",
             "gradient_evaluations": evals,
             "nuts_active_s": nuts_s,
@@ -567,7 +570,11 @@ def main():
                              "what": "counts + MAP + PMD/null NUTS on all positions + WAIC + predictive D_max, WITHOUT the forward-only / "
                                      "reverse-only refits of fits.py:298-356 (the north star's reduced unit; `value` above is the full fit); "
                                      "one step"},
-            "cfg3_full_pass": full_pass,
+            "cfg3_full_pass": full_pass if not steps_are_full_passes else {
+                "taxids": int(dev_fits / args.steps), "ms": dev_ms / args.steps, "value": dev_fits / (dev_ms * 1e-3), "unit": UNIT,
+                "steps": args.steps, "clocks": clocks,
+                "what": f"every timed step of this line is one pass over {n_full * world} fitted TaxIDs ({n_full} per GPU, cfg3 generator, "
+                        "seed 20240002, rank r = jumped block r), device resident: `value` / `ms_per_step` repeated"},
             "cpu_baseline": cpu,
             "kernel_ms_per_step": {"counts": per_step("counts_ms"), "map": per_step("map_ms"), "nuts": per_step("nuts_ms"),
                                    "nuts_union": per_step("nuts_union_ms"), "ppc": per_step("ppc_ms"), "assemble": per_step("assemble_ms")},

@@ -65,6 +65,7 @@ struct mdg_fit_lane {
     cudaEvent_t fork_ev = nullptr, join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     mdg::DevBuf rec, map, pred, counters, samples, waic, waic_acc[4];
     mdg::DevBuf chain_clock;  // development switch MDG_CHAIN_CLOCK=<file>
+    mdg::DevBuf order;        // queue order of the chunk's TaxIDs: [chunk] int order, [chunk] bucket bytes, 3 x kOrderBuckets counters
     int clock_items = 0;
     unsigned long long* h_leap = nullptr;  // pinned [MDG_NUM_RUNS]
     bool busy = false;
@@ -368,7 +369,7 @@ void mdg_ctx_destroy(mdg_ctx* ctx) {
     if (ctx->inputs_ready) cudaEventDestroy(ctx->inputs_ready);
     for (auto& ln : ctx->lane) {
         for (mdg::DevBuf* b : {&ln.rec, &ln.map, &ln.pred, &ln.counters, &ln.samples, &ln.waic, &ln.waic_acc[0], &ln.waic_acc[1],
-                               &ln.waic_acc[2], &ln.waic_acc[3], &ln.chain_clock})
+                               &ln.waic_acc[2], &ln.waic_acc[3], &ln.chain_clock, &ln.order})
             b->release();
         for (int i = 0; i < 5; ++i) if (ln.ev[i]) cudaEventDestroy(ln.ev[i]);
         if (ln.fork_ev) cudaEventDestroy(ln.fork_ev);
@@ -1211,6 +1212,28 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
         fl.da_sqrt = ctx->da_tables.as<double>(); fl.da_pow = fl.da_sqrt + kDaTable;
         fl.trace = d_trace ? d_trace + (size_t)c0 * MDG_NUM_RUNS * (W + S) * 4 : nullptr;
         for (int r = 0; r < MDG_NUM_RUNS; ++r) fl.sample_slot[r] = out_samples ? r : ((r & 1) ? -1 : r / 2);
+        // queue order: TaxIDs from both ends of the coverage range first (mdg_fit_kernels.cuh); MDG_NUTS_ORDER=0: input order
+        if (env_int("MDG_NUTS_ORDER", 1)) {
+            const size_t off_bucket = (size_t)chunk_max * sizeof(int), off_cnt = (off_bucket + (size_t)chunk_max + 15) & ~(size_t)15;
+            if ((rc = ln.order.ensure(off_cnt + 3 * kOrderBuckets * sizeof(unsigned int)))) return bail(rc);
+            int* d_order = ln.order.as<int>();
+            unsigned char* d_bucket = ln.order.as<unsigned char>() + off_bucket;
+            unsigned int* d_cnt = reinterpret_cast<unsigned int*>(ln.order.as<unsigned char>() + off_cnt);
+            MDG_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 3 * kOrderBuckets * sizeof(unsigned int), ls));
+            nuts_order_count_kernel<<<(nc + 255) / 256, 256, 0, ls>>>(fl.N, nc, R, d_bucket, d_cnt);
+            nuts_order_offsets_kernel<<<1, 32, 0, ls>>>(d_cnt);
+            nuts_order_scatter_kernel<<<(nc + 255) / 256, 256, 0, ls>>>(d_bucket, nc, d_cnt, d_order);
+            MDG_CUDA_TRY(cudaGetLastError());
+            ctx->timings.n_launches += 3;
+            fl.order = d_order;
+        }
+        // the forward / reverse runs of the first 1/16 of that order go before everything else: the worst stragglers
+        // measured (850 585 and 247 182 leapfrogs in one run; mean 9 800) are forward- or reverse-only runs of TaxIDs with
+        // 60-110 reads, and a chain that long must start at once to end inside its batch (profiles/r02_chain_timeline.md)
+        {
+            const int frac = env_int("MDG_NUTS_PRIO_FRAC", 16);
+            fl.n_prio = (fwd_rev && fl.order != nullptr && frac > 0) ? nc / frac : 0;
+        }
         if (getenv("MDG_CHAIN_CLOCK")) {
             if ((rc = ln.chain_clock.ensure((size_t)chunk_max * MDG_NUM_RUNS * 16))) return bail(rc);
             MDG_CUDA_TRY(cudaMemsetAsync(ln.chain_clock.ptr, 0, (size_t)nc * MDG_NUM_RUNS * 16, ls));
@@ -1233,12 +1256,12 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
             // PMD chains are long and heavy-tailed (adapted step size; max ~8x the mean), null chains
             // short and uniform: PMD first, null last fills the tail (profiles/r01_nuts_tuning.md).
             FitLaunch a = fl;  // PMD, all positions
-            a.n_items = nc; a.n_items_all = nc; a.work_counter = d_counters + 1;
+            a.n_items = nc; a.n_items_all = nc; a.n_prio = 0; a.work_counter = d_counters + 1;
             FitLaunch b = a;   // null, all positions
             b.work_counter = d_counters + 2;
             FitLaunch c = fl, d = fl;  // PMD / null, forward-only and reverse-only
             c.work_counter = d_counters + 3; d.work_counter = d_counters + 4;
-            c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_items_all = 0; d.n_items_all = 0;
+            c.n_items = 2 * nc; d.n_items = 2 * nc; c.n_items_all = 0; d.n_items_all = 0; c.n_prio = 0; d.n_prio = 0;
             const int gw_all = env_int("MDG_GW_ALL", 8), gw_half = env_int("MDG_GW_HALF", 8);  // lanes per chain (A/B runs: 16)
             if (fwd_rev && env_int("MDG_NUTS_MERGE", 1)) {
                 // One launch and ONE queue per model: the all-position runs first (the longest chains), then the
@@ -1246,6 +1269,7 @@ int mdg_fit_batch_submit(mdg_ctx* ctx, int mem, int64_t n_tax, int max_position,
                 // model's whole queue is empty, so the only hand-over between launches (CTA slots are released per CTA,
                 // i.e. when the last of its 16 chains ends) is PMD -> null.
                 a.n_items = 3 * nc; b.n_items = 3 * nc;
+                a.n_prio = fl.n_prio; b.n_prio = fl.n_prio;
                 if ((rc = launch_nuts_group_dispatch<0>(ctx, ln.side[3], a, ln.waic_acc[0], gw_all))) return bail(rc);
                 if ((rc = launch_nuts_group_dispatch<1>(ctx, ln.side[0], b, ln.waic_acc[1], gw_all))) return bail(rc);
             } else if (env_int("MDG_NUTS_A_FIRST", 1)) {

@@ -28,8 +28,10 @@ struct FitLaunch {
     int n_windows;
     int win_end[kMaxWindows];
     unsigned int* work_counter;
-    int n_items;        // items [0, n_items_all) are all-position runs (TaxID = item), the rest forward-only / reverse-only
-    int n_items_all;    // runs (TaxID = (item - n_items_all) / 2, mask 1 + (item - n_items_all) % 2): ONE queue, long chains first
+    int n_items;        // ONE queue per launch: n_items_all all-position runs (one per TaxID) and n_items - n_items_all
+    int n_items_all;    // forward-only / reverse-only runs (two per TaxID, mask 1 + (w & 1)), in three sections: the forward /
+    int n_prio;         // reverse runs of the first n_prio TaxIDs of `order`, every all-position run, the other forward / reverse runs
+    const int* order;   // [n_tax] queue position -> TaxID index of the chunk (nuts_order kernels), or NULL = identity
     RunRecord* rec;     // [n_tax][6]
     double* waic;       // [n_tax][6][2][2P]: lppd_i, pWAIC_i
     double* samples;    // [n_tax][sample_runs][S][4] constrained draws, or NULL
@@ -303,6 +305,57 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_MAP_MINBLOCKS) map_kernel(cons
         else map_fit_group<1, NPL>(ob, logC, p.P, p.pr, sh_prior[1], has_spare, lane, rec);
         if (lane == 0) p.rec[item] = rec;
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Queue order of a chunk's TaxIDs. The chains that decide when a batch ends sit at the two ends of the coverage
+// range: TaxIDs with a handful of reads (degenerate posteriors — adapted step sizes of 0.003-0.03 and 10^5..10^6
+// leapfrogs in one run, against a mean of 10^4) and, an order of magnitude less extreme, the TaxIDs with the most
+// reads (narrow posteriors). A chain is sequential, so the only thing a scheduler can do for them is start them
+// first: a counting sort over half-octave buckets of N_sum, the buckets taken from both ends towards the middle.
+// (Results do not depend on the order: every chain is keyed by (seed, tax_id, run).)
+// ---------------------------------------------------------------------------------------------
+constexpr int kOrderBuckets = 96;
+
+__device__ __forceinline__ int order_bucket(unsigned long long n_sum) {
+    if (n_sum < 2ull) return (int)n_sum;
+    const int lg = 63 - __clzll((long long)n_sum);
+    return min(kOrderBuckets - 1, 2 * lg + (int)((n_sum >> (lg - 1)) & 1ull));
+}
+
+// counters: [kOrderBuckets] histogram, then [kOrderBuckets] first queue position, then [kOrderBuckets] cursors
+__global__ void nuts_order_count_kernel(const uint32_t* __restrict__ N, int n_tax, int R, unsigned char* __restrict__ bucket,
+                                        unsigned int* __restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tax) return;
+    unsigned long long sum = 0;
+    for (int j = 0; j < R; ++j) sum += N[(size_t)i * R + j];
+    const int b = order_bucket(sum);
+    bucket[i] = (unsigned char)b;
+    atomicAdd(counters + b, 1u);
+}
+
+__global__ void nuts_order_offsets_kernel(unsigned int* __restrict__ counters) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int lo = 0, hi = kOrderBuckets - 1;
+    unsigned int pos = 0;
+    bool take_low = true;
+    while (lo <= hi) {
+        const int b = take_low ? lo++ : hi--;
+        counters[kOrderBuckets + b] = pos;
+        counters[2 * kOrderBuckets + b] = 0u;
+        if (counters[b] != 0u) take_low = !take_low;  // alternate only over buckets that hold TaxIDs
+        pos += counters[b];
+    }
+}
+
+__global__ void nuts_order_scatter_kernel(const unsigned char* __restrict__ bucket, int n_tax, unsigned int* __restrict__ counters,
+                                          int* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tax) return;
+    const int b = bucket[i];
+    order[counters[kOrderBuckets + b] + atomicAdd(counters + 2 * kOrderBuckets + b, 1u)] = i;
 }
 
 }  // namespace mdg

@@ -386,13 +386,13 @@ __global__ void __launch_bounds__(WARPS * 32, MDG_NUTS_MINBLOCKS * 4 / WARPS) nu
             if (item >= (unsigned)p.n_items) {
                 phase = GP_IDLE;
             } else {
-                if (item < (unsigned)p.n_items_all) {
-                    tax = (int)item;
-                    mask = 0;
-                } else {
-                    const unsigned h = item - (unsigned)p.n_items_all;
-                    tax = (int)(h >> 1);
-                    mask = 1 + (int)(h & 1u);
+                {
+                    const unsigned prio = 2u * (unsigned)p.n_prio, n_all = (unsigned)p.n_items_all;
+                    const bool is_all = item >= prio && item < prio + n_all;
+                    const unsigned w = is_all ? item - prio : (item < prio ? item : item - n_all);  // half runs: 2 * position + strand
+                    const unsigned q = is_all ? w : (w >> 1);  // queue position of the TaxID
+                    tax = p.order != nullptr ? __ldg(p.order + q) : (int)q;
+                    mask = is_all ? 0 : 1 + (int)(w & 1u);
                 }
                 run_kind = mask * 2 + MODEL;
                 n_obs = mask == 0 ? 2 * P : P;

@@ -48,3 +48,6 @@ for rank in range(int(lo), int(hi) + 1):
     print(f"rank {rank}: n_fit {len(L)} nuts_ms {best[0]:.1f} fit_ms {best[1]:.1f} wall_ms {best[2]:.1f} "
           f"mean_leapfrogs {L.mean():.0f} top4 {top.tolist()} longest: TaxID index {i} of {len(L)}, run {j}, "
           f"step size {out['result']['run']['step_size'][i, j]:.4g}", flush=True)
+    run = out["result"]["run"]
+    print(f"  longest chain's TaxID {int(r['tax_id'][i])}: k {r['k'][i].tolist()} N {r['N'][i].tolist()} leapfrogs per run {L[i].tolist()} "
+          f"divergent {run['n_divergent'][i].tolist()} accept {np.round(run['mean_accept'][i], 3).tolist()} step {np.round(run['step_size'][i], 5).tolist()}", flush=True)
