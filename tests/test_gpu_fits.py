@@ -321,6 +321,28 @@ def test_partition_and_order_invariance_bitwise(ctx):
     assert full["median"].tobytes() == chunked["median"].tobytes()
 
 
+def test_schedule_variants_are_bit_identical(ctx):
+    """How the chains are scheduled — one queue per model or four launches, the coverage order of the queue, which
+    forward / reverse runs go first, the shared-memory padding — must not change a single bit of the rows: every
+    chain is a function of (seed, tax_id, run, data) only."""
+    g = syn.make_mismatch_matrix(0, seed=77, n_fit=300)
+    r = ctx.counts_reduce(g["tax_id"], g["n_alignments"], g["is_reverse"], g["pos0"], g["counts16"], want_noise=True)
+    cfg = _lib.default_config(num_warmup=60, num_samples=80)
+    base = ctx.fit_batch(r["tax_id"], r["k"], r["N"], cfg, noise3=r["noise"], want_waic=True)
+    variants = [{"MDG_NUTS_ORDER": "0"}, {"MDG_NUTS_MERGE": "0"}, {"MDG_NUTS_MERGE": "0", "MDG_NUTS_A_FIRST": "0"},
+                {"MDG_NUTS_PRIO_FRAC": "1"}, {"MDG_NUTS_PRIO_FRAC": "0"}, {"MDG_NUTS_UNIFORM_SMEM": "0"}, {"MDG_FIT_CHUNK": "64"}]
+    for env in variants:
+        os.environ.update(env)
+        try:
+            got = ctx.fit_batch(r["tax_id"], r["k"], r["N"], cfg, noise3=r["noise"], want_waic=True)
+        finally:
+            for key in env:
+                del os.environ[key]
+        assert got["result"].tobytes() == base["result"].tobytes(), env
+        assert got["median"].tobytes() == base["median"].tobytes(), env
+        assert got["waic"].tobytes() == base["waic"].tobytes(), env
+
+
 @pytest.mark.parametrize("P", [25, 40])
 def test_other_max_positions(ctx, oracle, P):
     """BASELINE config 4: --max-position 25 with swapped substitutions: damage lives in CT/GA, so

@@ -275,3 +275,31 @@ def test_split_text_at_taxid_boundaries():
                 assert not (seen[i] & seen[j])
     big = text * 3  # large enough to be cut
     assert len(counts.split_text_at_taxid_boundaries(big, 4)) >= 2
+
+
+def test_decode_spans_and_pinned_file_reader(tmp_path):
+    """The counts seam cuts tax_name / tax_rank out of the file bytes through (offset, length) spans: one vectorised
+    gather for ASCII, string by string for anything else; the file text lands in a reusable staging buffer."""
+    text = "1\tHomo sapiens\tspecies\n2\tÆgir é\tgenus\n3\t\tno rank\n".encode("utf-8")
+    spans, pos = [], 0
+    for line in text.split(b"\n")[:-1]:
+        f = line.split(b"\t")
+        o1 = pos + len(f[0]) + 1
+        o2 = o1 + len(f[1]) + 1
+        spans.append(((o1, len(f[1])), (o2, len(f[2]))))
+        pos += len(line) + 1
+    names = counts._decode_spans(text, np.array([s[0] for s in spans]))
+    ranks = counts._decode_spans(np.frombuffer(text, np.uint8), np.array([s[1] for s in spans]))
+    assert names == ["Homo sapiens", "Ægir é", ""] and ranks == ["species", "genus", "no rank"]
+    assert counts._decode_spans(text, np.zeros((0, 2), np.int64)) == []
+    assert counts._decode_spans(b"abc def", np.array([[0, 3], [4, 3]])) == ["abc", "def"]  # the ASCII fast path
+    path = tmp_path / "table.txt"
+    path.write_bytes(text * 1000)
+    first = counts.read_file_bytes(str(path))
+    assert first.dtype == np.uint8 and first.tobytes() == text * 1000
+    path.write_bytes(text)
+    again = counts.read_file_bytes(str(path))  # a shorter file in the same buffer
+    assert again.tobytes() == text
+    # the TaxID-boundary split takes the byte array as well as bytes
+    big = b"".join(f"{t}\tn\tr\t10\t5'\t1".encode() + b"\t1" * 16 + b"\n" for t in range(3000) for _ in range(3))
+    assert counts.split_text_at_taxid_boundaries(big, 3) == counts.split_text_at_taxid_boundaries(np.frombuffer(big, np.uint8), 3)
