@@ -272,8 +272,10 @@ def _counts_piece_on_gpu(ctx, text, cfg):
 
 
 def _categorical_from_groups(values_per_group, group_of_row):
-    uniq, inv = np.unique(np.asarray(values_per_group, dtype=object), return_inverse=True)
-    return pd.Categorical.from_codes(inv[group_of_row], categories=uniq)
+    """per-TaxID strings -> the row-level categorical astype("category") would build (sorted categories), hashing
+    the n_tax strings once instead of sorting them or touching every row"""
+    per_group = pd.Categorical(np.asarray(values_per_group, dtype=object))
+    return pd.Categorical.from_codes(np.asarray(per_group.codes)[group_of_row], categories=per_group.categories)
 
 
 def _assemble_df_counts(pieces, cfg):

@@ -187,10 +187,10 @@ int launch_nuts_group(mdg_ctx* ctx, cudaStream_t st, FitLaunch fl, DevBuf& acc) 
     const int n_obs = fl.n_items_all > 0 ? 2 * fl.P : fl.P;  // the launch's longest run
     fl.n_slots = (n_obs + 1 + GW - 1) / GW;  // index 0 is the spare
     size_t smem = (size_t)WARPS * nuts_warp_smem_bytes(fl.n_slots);
-    // The four NUTS launches of a chunk take over each other's CTA slots as CTAs retire. Shared memory is allocated
+    // The NUTS launches of a chunk take over each other's CTA slots as CTAs retire. Shared memory is allocated
     // contiguously, so a retiring CTA's hole must fit the next launch's CTA: every launch asks for the same footprint
-    // (static + dynamic), the largest of the four (PMD, all positions). Otherwise the SMs end up with three resident
-    // CTAs instead of four (chain timeline in profiles/r02_nuts_tuning.md: 8 016 live chains instead of 9 472).
+    // (static + dynamic), the largest one (PMD with all-position runs). Otherwise the SMs end up with three resident
+    // CTAs instead of four (profiles/r02_chain_timeline.md: 8 016 live chains instead of 9 472).
     if (env_int("MDG_NUTS_UNIFORM_SMEM", 1)) {
         cudaFuncAttributes mine, big;
         MDG_CUDA_TRY(cudaFuncGetAttributes(&mine, kern));
@@ -199,11 +199,6 @@ int launch_nuts_group(mdg_ctx* ctx, cudaStream_t st, FitLaunch fl, DevBuf& acc) 
         if (want > mine.sharedSizeBytes + smem) smem = want - mine.sharedSizeBytes;
     }
     MDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // The same shared-memory carveout for every NUTS kernel: a launch whose preference differs from the previous
-    // launch's is a device-side synchronisation point (the null-model launches used to wait for the LAST chain of the
-    // PMD launches instead of taking over their CTA slots; chain timeline in profiles/r02_nuts_tuning.md).
-    if (env_int("MDG_NUTS_CARVEOUT", 1))
-        MDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // One group slot per item up to the whole GPU. (Smaller grids that leave every group several items were measured:
     // 3 / 6 / 12 items per group cost 14 / 21 / 39 % at 10 000 TaxIDs per batch and 0 / 9 / 35 % at 40 000 — fewer
     // resident chains, and different kernels sharing an SM's instruction cache; profiles/r02_nuts_tuning.md.)
