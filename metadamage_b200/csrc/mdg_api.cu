@@ -1033,7 +1033,8 @@ int harvest_lane(mdg_ctx* ctx, mdg_fit_lane& ln) {
     if (ln.clock_items > 0) {  // development: append this chunk's per-chain start / end times to the file MDG_CHAIN_CLOCK names
         std::vector<unsigned long long> h((size_t)ln.clock_items * 2);
         MDG_CUDA_TRY(cudaMemcpy(h.data(), ln.chain_clock.ptr, h.size() * 8, cudaMemcpyDeviceToHost));
-        if (FILE* f = fopen(getenv("MDG_CHAIN_CLOCK"), "ab")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        const char* path = getenv("MDG_CHAIN_CLOCK");
+        if (FILE* f = path ? fopen(path, "ab") : nullptr) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
         ln.clock_items = 0;
     }
     ln.busy = false;
