@@ -571,7 +571,7 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
         counts_scan_chunks_kernel<<<1, 32, 0, st>>>(d_chunk, n_chunks, d_ntax);
         MDG_CUDA_TRY(cudaGetLastError());
         ctx->timings.n_launches += 1;
-        counts_permute_kernel<<<(unsigned)((n_tiles + kPermuteWarps - 1) / kPermuteWarps), kPermuteWarps * 32, 0, st>>>(cp);
+        counts_permute_kernel<<<(unsigned)((n_tiles + kPermuteWarps * kPermuteTiles - 1) / (kPermuteWarps * kPermuteTiles)), kPermuteWarps * 32, 0, st>>>(cp);
         MDG_CUDA_TRY(cudaGetLastError());
         ctx->timings.n_launches += 3;
         if (cl.out_noise) {
@@ -643,7 +643,7 @@ int mdg_counts_reduce(mdg_ctx* ctx, int mem, int64_t n_rows, const int64_t* tax_
         MDG_CUDA_TRY(cudaGetLastError());
         counts_scan_kernel<<<1, 1024, 0, st>>>(d_tile_cnt, n_tiles, d_final_base, d_ntax);
         MDG_CUDA_TRY(cudaGetLastError());
-        counts_permute_kernel<<<(unsigned)((n_tiles + kPermuteWarps - 1) / kPermuteWarps), kPermuteWarps * 32, 0, st>>>(cp);
+        counts_permute_kernel<<<(unsigned)((n_tiles + kPermuteWarps * kPermuteTiles - 1) / (kPermuteWarps * kPermuteTiles)), kPermuteWarps * 32, 0, st>>>(cp);
         MDG_CUDA_TRY(cudaGetLastError());
         MDG_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
         ctx->timings.n_launches += 3;

@@ -584,22 +584,76 @@ struct CountsPermute {
 };
 
 constexpr int kPermuteWarps = 4;
+constexpr int kPermuteTiles = 8;  // consecutive tiles per warp (a divisor of kScanChunk): their blocks are adjacent in the output
 
-__global__ void __launch_bounds__(kPermuteWarps * 32) counts_permute_kernel(const CountsPermute p) {
-    // one warp per tile: a tile's block is a handful of TaxIDs, so the tiles must move in parallel
+// One warp moves the blocks of kPermuteTiles consecutive tiles. Their destinations are contiguous (the scan), so the
+// warp sees one output block of `total` per-TaxID rows whose sources are up to eight pieces; the tile bookkeeping is read
+// once (lanes 0-7) and handed round by shuffles, so no load depends on another load, and the k / N rows go four at a
+// time — all loads of a round are issued before its stores. (Round 2's first version ran one warp per tile: 78 125 tiny
+// warps = 19 532 CTAs for the 10M-row input, CTA dispatch alone took most of its 38 us.)
+__global__ void __launch_bounds__(kPermuteWarps * 32, 8) counts_permute_kernel(const CountsPermute p) {
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const long long t = (long long)blockIdx.x * kPermuteWarps + (threadIdx.x >> 5);
-    if (t >= p.n_tiles) return;
-    const int cnt = p.tile_cnt[t];
-    if (cnt == 0) return;
-    const long long src = p.tile_base[t], dst = p.final_base[t] + (p.chunk_off ? p.chunk_off[t / kScanChunk] : 0);
-    if (p.out_tax) for (int i = lane; i < cnt; i += 32) p.out_tax[dst + i] = p.t_tax[src + i];
-    if (p.out_nal) for (int i = lane; i < cnt; i += 32) p.out_nal[dst + i] = p.t_nal[src + i];
-    if (p.out_first) for (int i = lane; i < cnt; i += 32) p.out_first[dst + i] = p.t_first[src + i];
-    const long long nR = (long long)cnt * p.R;
-    if (p.out_k) for (long long i = lane; i < nR; i += 32) p.out_k[dst * p.R + i] = p.t_k[src * p.R + i];
-    if (p.out_N) for (long long i = lane; i < nR; i += 32) p.out_N[dst * p.R + i] = p.t_N[src * p.R + i];
-    if (p.out_noise) for (int i = lane; i < 3 * cnt; i += 32) p.out_noise[dst * 3 + i] = p.t_noise[src * 3 + i];
+    const long long t0 = ((long long)blockIdx.x * kPermuteWarps + (threadIdx.x >> 5)) * kPermuteTiles;
+    if (t0 >= p.n_tiles) return;
+    const long long t = t0 + (lane & (kPermuteTiles - 1));
+    int cnt = 0;
+    long long src = 0;
+    if (t < p.n_tiles) { cnt = __ldg(p.tile_cnt + t); src = __ldg(p.tile_base + t); }
+    const long long dst0 = __ldg(p.final_base + t0) + (p.chunk_off ? __ldg(p.chunk_off + t0 / kScanChunk) : 0);
+    int start[kPermuteTiles];
+    long long srcs[kPermuteTiles];
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < kPermuteTiles; ++i) {
+        srcs[i] = __shfl_sync(FULL, src, i);
+        start[i] = total;
+        total += __shfl_sync(FULL, cnt, i);
+    }
+    if (total == 0) return;
+    // source row of row j of the warp's output block (starts are non-decreasing: the last tile that starts at or
+    // before j owns it; empty tiles share their start with the next one and are overridden)
+    auto source_row = [&](int j) -> long long {
+        long long s = srcs[0];
+        int st = 0;
+#pragma unroll
+        for (int i = 1; i < kPermuteTiles; ++i)
+            if (j >= start[i]) { s = srcs[i]; st = start[i]; }
+        return s + (j - st);
+    };
+    for (int j = lane; j < total; j += 32) {
+        const long long s = source_row(j);
+        if (p.out_tax) p.out_tax[dst0 + j] = p.t_tax[s];
+        if (p.out_nal) p.out_nal[dst0 + j] = p.t_nal[s];
+        if (p.out_first) p.out_first[dst0 + j] = p.t_first[s];
+        if (p.out_noise) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p.out_noise[(dst0 + j) * 3 + c] = p.t_noise[s * 3 + c];
+        }
+    }
+    const int R = p.R;
+    for (int j0 = 0; j0 < total; j0 += 4) {
+        long long s[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] = j0 + u < total ? source_row(j0 + u) : -1;
+        for (int c = lane; c < R; c += 32) {
+            uint32_t a[4] = {0u, 0u, 0u, 0u}, b[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (s[u] >= 0) {
+                    if (p.out_k) a[u] = p.t_k[s[u] * R + c];
+                    if (p.out_N) b[u] = p.t_N[s[u] * R + c];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (s[u] >= 0) {
+                    if (p.out_k) p.out_k[(dst0 + j0 + u) * R + c] = a[u];
+                    if (p.out_N) p.out_N[(dst0 + j0 + u) * R + c] = b[u];
+                }
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
