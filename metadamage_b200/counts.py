@@ -106,8 +106,7 @@ def _decode_spans(text, spans):
     mat[col >= length[:, None]] = 0
     if mat.max() < 128 and not ((mat == 0) & (col < length[:, None])).any():
         return mat.view(f"S{longest}").ravel().astype(f"U{longest}").astype(object).tolist()
-    raw = bytes(memoryview(buf))
-    return [raw[int(o):int(o) + int(n)].decode("utf-8", "replace") for o, n in zip(off, length)]
+    return [buf[int(o):int(o) + int(n)].tobytes().decode("utf-8", "replace") for o, n in zip(off, length)]
 
 
 _TEXT_STAGE = {}  # one reusable page-locked staging buffer per process for the file text
