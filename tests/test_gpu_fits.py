@@ -329,8 +329,10 @@ def test_schedule_variants_are_bit_identical(ctx):
     r = ctx.counts_reduce(g["tax_id"], g["n_alignments"], g["is_reverse"], g["pos0"], g["counts16"], want_noise=True)
     cfg = _lib.default_config(num_warmup=60, num_samples=80)
     base = ctx.fit_batch(r["tax_id"], r["k"], r["N"], cfg, noise3=r["noise"], want_waic=True)
-    variants = [{"MDG_NUTS_ORDER": "0"}, {"MDG_NUTS_MERGE": "0"}, {"MDG_NUTS_MERGE": "0", "MDG_NUTS_A_FIRST": "0"},
-                {"MDG_NUTS_PRIO_FRAC": "1"}, {"MDG_NUTS_PRIO_FRAC": "0"}, {"MDG_NUTS_UNIFORM_SMEM": "0"}, {"MDG_FIT_CHUNK": "64"}]
+    # (the coverage order is the default from 32 768 TaxIDs per chunk on; MDG_NUTS_ORDER=2 forces it for this small batch)
+    variants = [{"MDG_NUTS_ORDER": "2"}, {"MDG_NUTS_ORDER": "2", "MDG_NUTS_PRIO_FRAC": "1"}, {"MDG_NUTS_ORDER": "2", "MDG_NUTS_PRIO_FRAC": "0"},
+                {"MDG_NUTS_ORDER": "2", "MDG_FIT_CHUNK": "64"}, {"MDG_NUTS_MERGE": "0"}, {"MDG_NUTS_MERGE": "0", "MDG_NUTS_A_FIRST": "0"},
+                {"MDG_NUTS_ORDER": "2", "MDG_NUTS_MERGE": "0"}, {"MDG_NUTS_UNIFORM_SMEM": "0"}, {"MDG_FIT_CHUNK": "64"}]
     for env in variants:
         os.environ.update(env)
         try:
