@@ -303,3 +303,22 @@ def test_decode_spans_and_pinned_file_reader(tmp_path):
     # the TaxID-boundary split takes the byte array as well as bytes
     big = b"".join(f"{t}\tn\tr\t10\t5'\t1".encode() + b"\t1" * 16 + b"\n" for t in range(3000) for _ in range(3))
     assert counts.split_text_at_taxid_boundaries(big, 3) == counts.split_text_at_taxid_boundaries(np.frombuffer(big, np.uint8), 3)
+
+
+def test_bench_workloads_follow_baseline_configs():
+    """N = 1 is BASELINE config 2 (10 000 fitted TaxIDs, seed 20240001); N > 1 steps over config 3's per-GPU share
+    (seed 20240002, 125 000 TaxIDs per GPU = 1M over 8 GPUs), the same description for both arms."""
+    import argparse
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
+    one = bench.workload_config(argparse.Namespace(max_position=15, taxa_per_gpu=10_000, inflight=1), 1)
+    assert "cfg2" in one["workload"] and "20240001" in one["workload"] and one["taxa_per_gpu"] == 10_000
+    eight = bench.workload_config(argparse.Namespace(max_position=15, taxa_per_gpu=125_000, inflight=1), 8)
+    assert "cfg3" in eight["workload"] and "20240002" in eight["workload"] and "over 8 GPUs" in eight["workload"]
+    assert eight["taxa_per_gpu"] * 8 == 1_000_000 and "model" not in eight
+    src = open(os.path.join(root, "bench.py")).read()
+    assert src.count("125_000") >= 2  # the default of both arms
